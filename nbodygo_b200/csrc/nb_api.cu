@@ -1,0 +1,693 @@
+// nb_api.cu — host side of libnbody_b200.so: the C ABI of include/nbody_b200.h.
+//
+// One nb_sim owns the device image of BodyCollection.arr (cmd/body/body_collection.go:16)
+// on one GPU, a stream, and (optionally) an NCCL communicator.  nb_step enqueues
+//   K0 prep → K1 force+detect → [exchange pairs] → K3 resolve → K4 integrate → [exchange state]
+// on the handle's stream — the block cmd/runner/computation-runner.go:285-320.
+// There is no CPU fallback anywhere in this file: without a device every entry
+// point fails with NB_ERR_NO_DEVICE / NB_ERR_CUDA.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <dlfcn.h>
+#include <string>
+#include <vector>
+
+#include "nb_internal.cuh"
+
+using namespace nb;
+
+// ---------------------------------------------------------------- NCCL (dlopen)
+namespace {
+struct NcclUid { char internal[128]; };
+typedef void *NcclComm;
+struct NcclApi {
+    void *lib = nullptr;
+    int (*GetUniqueId)(NcclUid *) = nullptr;
+    int (*CommInitRank)(NcclComm *, int, NcclUid, int) = nullptr;
+    int (*CommDestroy)(NcclComm) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, NcclComm, cudaStream_t) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+    bool ok = false;
+};
+NcclApi g_nccl;
+constexpr int NCCL_UINT8 = 1, NCCL_UINT32 = 3, NCCL_UINT64 = 5, NCCL_FLOAT64 = 8;
+
+bool load_nccl(std::string &err)
+{
+    if (g_nccl.ok) return true;
+    const char *names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char *nm : names) {
+        g_nccl.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (g_nccl.lib) break;
+    }
+    if (!g_nccl.lib) { err = std::string("dlopen libnccl.so.2 failed: ") + dlerror(); return false; }
+#define NB_SYM(field, name)                                                   \
+    *(void **)(&g_nccl.field) = dlsym(g_nccl.lib, name);                      \
+    if (!g_nccl.field) { err = std::string("missing NCCL symbol ") + name; return false; }
+    NB_SYM(GetUniqueId, "ncclGetUniqueId")
+    NB_SYM(CommInitRank, "ncclCommInitRank")
+    NB_SYM(CommDestroy, "ncclCommDestroy")
+    NB_SYM(AllGather, "ncclAllGather")
+    NB_SYM(GroupStart, "ncclGroupStart")
+    NB_SYM(GroupEnd, "ncclGroupEnd")
+    NB_SYM(GetErrorString, "ncclGetErrorString")
+#undef NB_SYM
+    g_nccl.ok = true;
+    return true;
+}
+std::string g_create_err;
+}  // namespace
+
+// ---------------------------------------------------------------- handle
+struct nb_sim {
+    int device = 0;
+    long long cap = 0, cap_pad = 0, n = 0;
+    long long seg_cap = 0, hev_cap = 0;
+    DevState d{};
+    // partial sums (grown on demand)
+    long long part_elems = 0;
+    // compaction scratch
+    double *scratch_f64 = nullptr;
+    uint8_t *scratch_u8 = nullptr;
+    long long *d_map = nullptr, *d_new_n = nullptr;
+    unsigned *d_block_sums = nullptr;
+    unsigned long long *d_pair_counts = nullptr;
+    Counters *h_ctr = nullptr;                 // pinned
+    unsigned long long *h_counts = nullptr;    // pinned [MAX_RANKS]
+    long long *h_new_n = nullptr;              // pinned
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev[7] = {};
+    int rank = 0, nranks = 1;
+    NcclComm comm = nullptr;
+    std::string err;
+    nb_step_result last{};
+    bool pending = false;
+    bool stepped = false;
+    unsigned last_opts = 0;
+    long long launches = 0;
+    int force_R = 0;
+    StepParams last_params{};
+};
+
+#define NB_CUDA(h, call)                                                                              \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess) {                                                                      \
+            (h)->err = std::string(#call) + ": " + cudaGetErrorString(e_);                            \
+            return NB_ERR_CUDA;                                                                       \
+        }                                                                                             \
+    } while (0)
+
+#define NB_NCCL(h, call)                                                                              \
+    do {                                                                                              \
+        int r_ = (call);                                                                              \
+        if (r_ != 0) {                                                                                \
+            (h)->err = std::string(#call) + ": " + g_nccl.GetErrorString(r_);                         \
+            return NB_ERR_COMM;                                                                       \
+        }                                                                                             \
+    } while (0)
+
+static int fail(nb_handle h, int code, const std::string &msg)
+{
+    if (h) h->err = msg; else g_create_err = msg;
+    return code;
+}
+
+static long long round_up(long long v, long long m) { return (v + m - 1) / m * m; }
+
+static double **f64_fields(DevState &d, int k)
+{
+    double **f[] = {&d.x, &d.y, &d.z, &d.vx, &d.vy, &d.vz, &d.mass, &d.radius, &d.rest, &d.ff, &d.fs};
+    return f[k];
+}
+constexpr int N_F64 = 11;
+
+extern "C" int nb_abi_version(void) { return NB_ABI_VERSION; }
+
+extern "C" const char *nb_last_error(nb_handle h) { return h ? h->err.c_str() : g_create_err.c_str(); }
+
+static void free_all(nb_handle h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->st) cudaStreamSynchronize(h->st);
+    if (h->comm && g_nccl.ok) g_nccl.CommDestroy(h->comm);
+    for (int k = 0; k < N_F64; ++k) cudaFree(*f64_fields(h->d, k));
+    cudaFree(h->d.jm); cudaFree(h->d.fx); cudaFree(h->d.fy); cudaFree(h->d.fz);
+    cudaFree(h->d.behavior); cudaFree(h->d.flags); cudaFree(h->d.tile_rmax);
+    cudaFree(h->d.px); cudaFree(h->d.py); cudaFree(h->d.pz);
+    cudaFree(h->d.render); cudaFree(h->d.render_exists);
+    if (h->d.pairs_all != h->d.pairs) cudaFree(h->d.pairs_all);
+    cudaFree(h->d.pairs); cudaFree(h->d.hev); cudaFree(h->d.head); cudaFree(h->d.ctr);
+    cudaFree(h->scratch_f64); cudaFree(h->scratch_u8); cudaFree(h->d_map); cudaFree(h->d_new_n);
+    cudaFree(h->d_block_sums); cudaFree(h->d_pair_counts);
+    if (h->h_ctr) cudaFreeHost(h->h_ctr);
+    if (h->h_counts) cudaFreeHost(h->h_counts);
+    if (h->h_new_n) cudaFreeHost(h->h_new_n);
+    for (auto &e : h->ev) if (e) cudaEventDestroy(e);
+    if (h->st) cudaStreamDestroy(h->st);
+    delete h;
+}
+
+extern "C" int nb_create(int device, int64_t capacity, int64_t pair_capacity, nb_handle *out)
+{
+    if (!out || capacity < 0) return fail(nullptr, NB_ERR_INVALID, "nb_create: bad arguments");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, NB_ERR_NO_DEVICE,
+                    std::string("no CUDA device (there is no CPU fallback): ") + cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(nullptr, NB_ERR_INVALID, "nb_create: device out of range");
+    nb_sim *h = new nb_sim();
+    h->device = device;
+    h->cap = capacity;
+    h->cap_pad = round_up(capacity + MAX_RANKS, TJ);
+    h->seg_cap = pair_capacity > 0 ? pair_capacity : 4 * capacity + 65536;
+    h->hev_cap = h->seg_cap;
+    if (const char *fr = getenv("NB_FORCE_R")) h->force_R = atoi(fr);
+    auto bail = [&](const char *what, cudaError_t ce) {
+        g_create_err = std::string(what) + ": " + cudaGetErrorString(ce);
+        free_all(h);
+        return NB_ERR_CUDA;
+    };
+#define NB_TRY(call)                                   \
+    do {                                               \
+        cudaError_t ce_ = (call);                      \
+        if (ce_ != cudaSuccess) return bail(#call, ce_); \
+    } while (0)
+    NB_TRY(cudaSetDevice(device));
+    NB_TRY(cudaStreamCreateWithFlags(&h->st, cudaStreamNonBlocking));
+    for (auto &evn : h->ev) NB_TRY(cudaEventCreate(&evn));
+    const size_t fb = (size_t)h->cap_pad * sizeof(double);
+    for (int k = 0; k < N_F64; ++k) {
+        NB_TRY(cudaMalloc((void **)f64_fields(h->d, k), fb));
+        NB_TRY(cudaMemsetAsync(*f64_fields(h->d, k), 0, fb, h->st));
+    }
+    NB_TRY(cudaMalloc((void **)&h->d.jm, fb));
+    NB_TRY(cudaMalloc((void **)&h->d.fx, fb));
+    NB_TRY(cudaMalloc((void **)&h->d.fy, fb));
+    NB_TRY(cudaMalloc((void **)&h->d.fz, fb));
+    NB_TRY(cudaMemsetAsync(h->d.fx, 0, fb, h->st));
+    NB_TRY(cudaMemsetAsync(h->d.fy, 0, fb, h->st));
+    NB_TRY(cudaMemsetAsync(h->d.fz, 0, fb, h->st));
+    NB_TRY(cudaMalloc((void **)&h->d.behavior, (size_t)h->cap_pad));
+    NB_TRY(cudaMalloc((void **)&h->d.flags, (size_t)h->cap_pad));
+    NB_TRY(cudaMemsetAsync(h->d.behavior, 0, (size_t)h->cap_pad, h->st));
+    NB_TRY(cudaMemsetAsync(h->d.flags, 0, (size_t)h->cap_pad, h->st));
+    NB_TRY(cudaMalloc((void **)&h->d.tile_rmax, (size_t)(h->cap_pad / TJ) * sizeof(double)));
+    NB_TRY(cudaMalloc((void **)&h->d.render, (size_t)h->cap_pad * 3 * sizeof(float)));
+    NB_TRY(cudaMalloc((void **)&h->d.render_exists, (size_t)h->cap_pad));
+    NB_TRY(cudaMemsetAsync(h->d.render, 0, (size_t)h->cap_pad * 3 * sizeof(float), h->st));
+    NB_TRY(cudaMemsetAsync(h->d.render_exists, 0, (size_t)h->cap_pad, h->st));
+    NB_TRY(cudaMalloc((void **)&h->d.pairs, (size_t)h->seg_cap * sizeof(int2)));
+    NB_TRY(cudaMalloc((void **)&h->d.hev, (size_t)h->hev_cap * sizeof(nb_event)));
+    NB_TRY(cudaMalloc((void **)&h->d.head, (size_t)h->cap_pad * sizeof(unsigned long long)));
+    NB_TRY(cudaMemsetAsync(h->d.head, 0, (size_t)h->cap_pad * sizeof(unsigned long long), h->st));
+    NB_TRY(cudaMalloc((void **)&h->d.ctr, sizeof(Counters)));
+    NB_TRY(cudaMemsetAsync(h->d.ctr, 0, sizeof(Counters), h->st));
+    NB_TRY(cudaMalloc((void **)&h->scratch_f64, fb));
+    NB_TRY(cudaMalloc((void **)&h->scratch_u8, (size_t)h->cap_pad));
+    NB_TRY(cudaMalloc((void **)&h->d_map, (size_t)h->cap_pad * sizeof(long long)));
+    NB_TRY(cudaMalloc((void **)&h->d_new_n, sizeof(long long)));
+    NB_TRY(cudaMalloc((void **)&h->d_block_sums, (size_t)(h->cap_pad / 1024 + 2) * sizeof(unsigned)));
+    NB_TRY(cudaMalloc((void **)&h->d_pair_counts, MAX_RANKS * sizeof(unsigned long long)));
+    NB_TRY(cudaMemsetAsync(h->d_pair_counts, 0, MAX_RANKS * sizeof(unsigned long long), h->st));
+    h->d.pair_counts = h->d_pair_counts;
+    h->d.pairs_all = h->d.pairs;
+    NB_TRY(cudaMallocHost((void **)&h->h_ctr, sizeof(Counters)));
+    NB_TRY(cudaMallocHost((void **)&h->h_counts, MAX_RANKS * sizeof(unsigned long long)));
+    NB_TRY(cudaMallocHost((void **)&h->h_new_n, sizeof(long long)));
+    NB_TRY(cudaStreamSynchronize(h->st));
+#undef NB_TRY
+    *out = h;
+    return NB_OK;
+}
+
+extern "C" int nb_destroy(nb_handle h)
+{
+    if (!h) return NB_ERR_INVALID;
+    free_all(h);
+    return NB_OK;
+}
+
+// ---------------------------------------------------------------- state sync
+static int copy_in_f64(nb_handle h, double *dst, const double *src, long long first, long long count, double dflt,
+                       bool use_default)
+{
+    if (src) {
+        NB_CUDA(h, cudaMemcpyAsync(dst + first, src, (size_t)count * sizeof(double), cudaMemcpyHostToDevice, h->st));
+    } else if (use_default) {
+        h->launches += launch_fill_f64(dst + first, dflt, count, h->st);
+    }
+    return NB_OK;
+}
+static int copy_in_u8(nb_handle h, uint8_t *dst, const uint8_t *src, long long first, long long count, uint8_t dflt,
+                      bool use_default)
+{
+    if (src) {
+        NB_CUDA(h, cudaMemcpyAsync(dst + first, src, (size_t)count, cudaMemcpyHostToDevice, h->st));
+    } else if (use_default) {
+        h->launches += launch_fill_u8(dst + first, dflt, count, h->st);
+    }
+    return NB_OK;
+}
+
+static int write_range(nb_handle h, long long first, long long count, bool defaults, double rest_default,
+                       const double *x, const double *y, const double *z, const double *vx, const double *vy,
+                       const double *vz, const double *mass, const double *radius, const double *rest,
+                       const double *ff, const double *fs, const uint8_t *behavior, const uint8_t *flags)
+{
+    if (count == 0) return NB_OK;
+    NB_CUDA(h, cudaSetDevice(h->device));
+    const double *src[N_F64] = {x, y, z, vx, vy, vz, mass, radius, rest, ff, fs};
+    const double dfl[N_F64] = {0, 0, 0, 0, 0, 0, 0, 0, rest_default, 0, 0};
+    for (int k = 0; k < N_F64; ++k) {
+        int rc = copy_in_f64(h, *f64_fields(h->d, k), src[k], first, count, dfl[k], defaults);
+        if (rc) return rc;
+    }
+    int rc = copy_in_u8(h, h->d.behavior, behavior, first, count, NB_ELASTIC, defaults);
+    if (rc) return rc;
+    rc = copy_in_u8(h, h->d.flags, flags, first, count, NB_F_EXISTS, defaults);
+    if (rc) return rc;
+    // host buffers may be reused by the caller as soon as we return
+    NB_CUDA(h, cudaStreamSynchronize(h->st));
+    return NB_OK;
+}
+
+extern "C" int nb_upload(nb_handle h, int64_t n, const double *x, const double *y, const double *z, const double *vx,
+                         const double *vy, const double *vz, const double *mass, const double *radius,
+                         const double *restitution, const double *frag_factor, const double *frag_step,
+                         const uint8_t *behavior, const uint8_t *flags)
+{
+    if (!h || n < 0) return fail(h, NB_ERR_INVALID, "nb_upload: bad arguments");
+    if (n > h->cap) return fail(h, NB_ERR_CAPACITY, "nb_upload: n exceeds capacity");
+    if (n > 0 && (!x || !y || !z || !vx || !vy || !vz || !mass || !radius))
+        return fail(h, NB_ERR_INVALID, "nb_upload: x,y,z,vx,vy,vz,mass,radius are required");
+    h->n = n;
+    h->stepped = false;
+    return write_range(h, 0, n, true, 1.0, x, y, z, vx, vy, vz, mass, radius, restitution, frag_factor, frag_step,
+                       behavior, flags);
+}
+
+extern "C" int nb_patch(nb_handle h, int64_t first, int64_t count, const double *x, const double *y, const double *z,
+                        const double *vx, const double *vy, const double *vz, const double *mass,
+                        const double *radius, const double *restitution, const double *frag_factor,
+                        const double *frag_step, const uint8_t *behavior, const uint8_t *flags)
+{
+    if (!h || first < 0 || count < 0 || first + count > h->n) return fail(h, NB_ERR_INVALID, "nb_patch: bad range");
+    return write_range(h, first, count, false, 0.0, x, y, z, vx, vy, vz, mass, radius, restitution, frag_factor,
+                       frag_step, behavior, flags);
+}
+
+extern "C" int nb_append(nb_handle h, int64_t count, double R, const double *x, const double *y, const double *z,
+                         const double *vx, const double *vy, const double *vz, const double *mass,
+                         const double *radius, const double *frag_factor, const double *frag_step,
+                         const uint8_t *behavior, const uint8_t *flags)
+{
+    if (!h || count < 0) return fail(h, NB_ERR_INVALID, "nb_append: bad arguments");
+    if (h->n + count > h->cap) return fail(h, NB_ERR_CAPACITY, "nb_append: capacity exceeded");
+    if (count > 0 && (!x || !y || !z || !vx || !vy || !vz || !mass || !radius))
+        return fail(h, NB_ERR_INVALID, "nb_append: x,y,z,vx,vy,vz,mass,radius are required");
+    // arr[j].r = R for every added body (body_collection.go:276,288)
+    int rc = write_range(h, h->n, count, true, R, x, y, z, vx, vy, vz, mass, radius, nullptr, frag_factor, frag_step,
+                         behavior, flags);
+    if (rc) return rc;
+    h->n += count;
+    return NB_OK;
+}
+
+extern "C" int nb_count(nb_handle h, int64_t *n)
+{
+    if (!h || !n) return NB_ERR_INVALID;
+    *n = h->n;
+    return NB_OK;
+}
+
+extern "C" int nb_compact(nb_handle h, int64_t *n_out, int64_t *old_index, int64_t old_index_cap)
+{
+    if (!h) return NB_ERR_INVALID;
+    NB_CUDA(h, cudaSetDevice(h->device));
+    const long long n_old = h->n;
+    h->launches += launch_compact_map(h->d, n_old, h->d_map, h->d_block_sums, h->d_new_n, h->st);
+    for (int k = 0; k < N_F64; ++k) {
+        double **f = f64_fields(h->d, k);
+        h->launches += launch_gather_f64(*f, h->scratch_f64, h->d_map, h->d_new_n, n_old, h->st);
+        std::swap(*f, h->scratch_f64);
+    }
+    double **outs[] = {&h->d.fx, &h->d.fy, &h->d.fz};
+    for (auto f : outs) {
+        h->launches += launch_gather_f64(*f, h->scratch_f64, h->d_map, h->d_new_n, n_old, h->st);
+        std::swap(*f, h->scratch_f64);
+    }
+    h->launches += launch_gather_u8(h->d.behavior, h->scratch_u8, h->d_map, h->d_new_n, n_old, h->st);
+    std::swap(h->d.behavior, h->scratch_u8);
+    h->launches += launch_gather_u8(h->d.flags, h->scratch_u8, h->d_map, h->d_new_n, n_old, h->st);
+    std::swap(h->d.flags, h->scratch_u8);
+    NB_CUDA(h, cudaMemcpyAsync(h->h_new_n, h->d_new_n, sizeof(long long), cudaMemcpyDeviceToHost, h->st));
+    NB_CUDA(h, cudaStreamSynchronize(h->st));
+    const long long n_new = n_old > 0 ? *h->h_new_n : 0;
+    if (old_index) {
+        const long long m = std::min<long long>(n_new, old_index_cap);
+        static_assert(sizeof(long long) == sizeof(int64_t), "int64");
+        NB_CUDA(h, cudaMemcpy(old_index, h->d_map, (size_t)m * sizeof(long long), cudaMemcpyDeviceToHost));
+    }
+    h->n = n_new;
+    h->stepped = false;  // pair / event indices of the last step no longer match the array
+    if (n_out) *n_out = n_new;
+    return NB_OK;
+}
+
+// ---------------------------------------------------------------- step
+static void chunking(long long n, int &n_tiles, int &n_chunks, int &tiles_per_chunk)
+{
+    // a function of n only: the per-body summation order never depends on the grid or the rank count
+    n_tiles = (int)((n + TJ - 1) / TJ);
+    int s = std::min(n_tiles, MAX_CHUNKS);
+    if (s < 1) s = 1;
+    tiles_per_chunk = (n_tiles + s - 1) / s;
+    if (tiles_per_chunk < 1) tiles_per_chunk = 1;
+    n_chunks = n_tiles > 0 ? (n_tiles + tiles_per_chunk - 1) / tiles_per_chunk : 1;
+}
+
+static int ensure_partials(nb_handle h, long long elems)
+{
+    if (elems <= h->part_elems) return NB_OK;
+    cudaFree(h->d.px); cudaFree(h->d.py); cudaFree(h->d.pz);
+    h->d.px = h->d.py = h->d.pz = nullptr;
+    h->part_elems = 0;
+    NB_CUDA(h, cudaMalloc((void **)&h->d.px, (size_t)elems * sizeof(double)));
+    NB_CUDA(h, cudaMalloc((void **)&h->d.py, (size_t)elems * sizeof(double)));
+    NB_CUDA(h, cudaMalloc((void **)&h->d.pz, (size_t)elems * sizeof(double)));
+    h->part_elems = elems;
+    return NB_OK;
+}
+
+static int finish_step(nb_handle h, nb_step_result *out)
+{
+    NB_CUDA(h, cudaSetDevice(h->device));
+    NB_CUDA(h, cudaStreamSynchronize(h->st));
+    if (h->pending) {
+        const Counters &c = *h->h_ctr;
+        nb_step_result r{};
+        r.n_bodies = h->n;
+        r.n_pairs = (h->last_opts & NB_STEP_COLLISIONS) ? c.total_pairs : 0;
+        r.n_host_events = (int64_t)std::min<unsigned long long>(c.n_hev, (unsigned long long)h->hev_cap);
+        r.n_resolved = (int64_t)c.n_resolved;
+        r.n_culled = (int64_t)c.n_culled;
+        r.n_dead = (int64_t)c.n_dead;
+        r.resolve_rounds = c.rounds;
+        r.pair_overflow = c.overflow ? 1 : (c.n_hev > (unsigned long long)h->hev_cap ? 2 : 0);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, h->ev[0], h->ev[6]); r.ms_total = ms;
+        cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]); r.ms_prep = ms;
+        cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]); r.ms_force = ms;
+        cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]); r.ms_exchange = ms;
+        cudaEventElapsedTime(&ms, h->ev[3], h->ev[4]); r.ms_resolve = ms;
+        cudaEventElapsedTime(&ms, h->ev[4], h->ev[5]); r.ms_integrate = ms;
+        float ms2 = 0;
+        cudaEventElapsedTime(&ms2, h->ev[5], h->ev[6]); r.ms_exchange += ms2;
+        h->last = r;
+        h->pending = false;
+    }
+    if (out) *out = h->last;
+    if (h->last.pair_overflow == 1)
+        return fail(h, NB_ERR_PAIR_OVERFLOW, "collision pair capacity exceeded; step not applied");
+    return NB_OK;
+}
+
+extern "C" int nb_sync(nb_handle h, nb_step_result *out)
+{
+    if (!h) return NB_ERR_INVALID;
+    return finish_step(h, out);
+}
+
+static int exchange_pairs(nb_handle h, StepParams &p)
+{
+    // counts first (8 bytes per rank), then the first `mx` entries of every rank's list
+    NB_NCCL(h, g_nccl.AllGather(&h->d.ctr->n_pairs, h->d_pair_counts, 1, NCCL_UINT64, h->comm, h->st));
+    NB_CUDA(h, cudaMemcpyAsync(h->h_counts, h->d_pair_counts, h->nranks * sizeof(unsigned long long),
+                               cudaMemcpyDeviceToHost, h->st));
+    NB_CUDA(h, cudaStreamSynchronize(h->st));
+    unsigned long long mx = 0;
+    for (int r = 0; r < h->nranks; ++r) mx = std::max(mx, h->h_counts[r]);
+    mx = std::min<unsigned long long>(mx, (unsigned long long)h->seg_cap);
+    p.seg_stride = (long long)std::max<unsigned long long>(mx, 1ull);
+    if (mx > 0)
+        NB_NCCL(h, g_nccl.AllGather(h->d.pairs, h->d.pairs_all, (size_t)mx * 2, NCCL_UINT32, h->comm, h->st));
+    return NB_OK;
+}
+
+extern "C" int nb_step(nb_handle h, double time_scaling, double R, uint32_t opts, nb_step_result *out)
+{
+    if (!h) return NB_ERR_INVALID;
+    if (h->pending) {
+        int rc = finish_step(h, nullptr);
+        if (rc) return rc;
+    }
+    NB_CUDA(h, cudaSetDevice(h->device));
+    StepParams p{};
+    p.n = h->n;
+    chunking(h->n, p.n_tiles, p.n_chunks, p.tiles_per_chunk);
+    const long long shard = (h->n + h->nranks - 1) / h->nranks;
+    p.i0 = std::min<long long>(h->n, (long long)h->rank * shard);
+    p.i1 = std::min<long long>(h->n, p.i0 + shard);
+    p.n_pad_local = round_up(std::max<long long>(p.i1 - p.i0, 1), 32);
+    p.rank = h->rank;
+    p.nranks = h->nranks;
+    p.seg_cap = h->seg_cap;
+    p.hev_cap = h->hev_cap;
+    p.opts = opts;
+    p.ts = time_scaling;
+    p.R = R;
+    int rc = ensure_partials(h, (long long)p.n_chunks * p.n_pad_local);
+    if (rc) return rc;
+    h->d.pair_counts = h->d_pair_counts;
+    p.seg_stride = h->seg_cap;
+    p.s = h->d;
+
+    NB_CUDA(h, cudaEventRecord(h->ev[0], h->st));
+    NB_CUDA(h, cudaMemsetAsync(h->d.ctr, 0, sizeof(Counters), h->st));
+    h->launches += launch_prep(p, h->st);
+    NB_CUDA(h, cudaEventRecord(h->ev[1], h->st));
+    h->launches += launch_force(p, h->st, h->force_R);
+    NB_CUDA(h, cudaEventRecord(h->ev[2], h->st));
+    if (h->nranks > 1 && (opts & NB_STEP_COLLISIONS)) {
+        rc = exchange_pairs(h, p);
+        if (rc) return rc;
+    }
+    NB_CUDA(h, cudaEventRecord(h->ev[3], h->st));
+    if (opts & NB_STEP_COLLISIONS) h->launches += launch_resolve(p, h->st);
+    NB_CUDA(h, cudaEventRecord(h->ev[4], h->st));
+    h->launches += launch_integrate(p, h->st);
+    NB_CUDA(h, cudaEventRecord(h->ev[5], h->st));
+    if (h->nranks > 1) {
+        if (!(opts & NB_STEP_NO_INTEGRATE)) {
+            NB_NCCL(h, g_nccl.GroupStart());
+            double *arrs[] = {h->d.x, h->d.y, h->d.z, h->d.vx, h->d.vy, h->d.vz, h->d.rest};
+            for (double *a : arrs)
+                NB_NCCL(h, g_nccl.AllGather(a + (long long)h->rank * shard, a, (size_t)shard, NCCL_FLOAT64, h->comm,
+                                            h->st));
+            NB_NCCL(h, g_nccl.AllGather(h->d.flags + (long long)h->rank * shard, h->d.flags, (size_t)shard,
+                                        NCCL_UINT8, h->comm, h->st));
+            NB_NCCL(h, g_nccl.GroupEnd());
+        }
+        h->launches += launch_count_dead(p, h->st);
+    }
+    NB_CUDA(h, cudaEventRecord(h->ev[6], h->st));
+    NB_CUDA(h, cudaMemcpyAsync(h->h_ctr, h->d.ctr, sizeof(Counters), cudaMemcpyDeviceToHost, h->st));
+    NB_CUDA(h, cudaGetLastError());
+    h->pending = true;
+    h->stepped = true;
+    h->last_opts = opts;
+    h->last_params = p;
+    if (opts & NB_STEP_ASYNC) return NB_OK;
+    return finish_step(h, out);
+}
+
+// ---------------------------------------------------------------- results
+static int copy_out(nb_handle h, void *dst, const void *src, size_t bytes)
+{
+    if (!dst || bytes == 0) return NB_OK;
+    NB_CUDA(h, cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, h->st));
+    return NB_OK;
+}
+
+extern "C" int nb_download_state(nb_handle h, double *x, double *y, double *z, double *vx, double *vy, double *vz,
+                                 double *mass, double *radius, double *restitution, uint8_t *behavior,
+                                 uint8_t *flags)
+{
+    if (!h) return NB_ERR_INVALID;
+    NB_CUDA(h, cudaSetDevice(h->device));
+    const size_t fb = (size_t)h->n * sizeof(double);
+    double *dst[] = {x, y, z, vx, vy, vz, mass, radius, restitution};
+    for (int k = 0; k < 9; ++k) {
+        int rc = copy_out(h, dst[k], *f64_fields(h->d, k), fb);
+        if (rc) return rc;
+    }
+    int rc = copy_out(h, behavior, h->d.behavior, (size_t)h->n);
+    if (rc) return rc;
+    rc = copy_out(h, flags, h->d.flags, (size_t)h->n);
+    if (rc) return rc;
+    NB_CUDA(h, cudaStreamSynchronize(h->st));
+    return NB_OK;
+}
+
+extern "C" int nb_download_render(nb_handle h, float *xyz, uint8_t *exists)
+{
+    if (!h) return NB_ERR_INVALID;
+    NB_CUDA(h, cudaSetDevice(h->device));
+    int rc = copy_out(h, xyz, h->d.render, (size_t)h->n * 3 * sizeof(float));
+    if (rc) return rc;
+    rc = copy_out(h, exists, h->d.render_exists, (size_t)h->n);
+    if (rc) return rc;
+    NB_CUDA(h, cudaStreamSynchronize(h->st));
+    return NB_OK;
+}
+
+extern "C" int nb_get_forces(nb_handle h, double *fx, double *fy, double *fz)
+{
+    if (!h) return NB_ERR_INVALID;
+    NB_CUDA(h, cudaSetDevice(h->device));
+    const size_t fb = (size_t)h->n * sizeof(double);
+    int rc = copy_out(h, fx, h->d.fx, fb);
+    if (!rc) rc = copy_out(h, fy, h->d.fy, fb);
+    if (!rc) rc = copy_out(h, fz, h->d.fz, fb);
+    if (rc) return rc;
+    NB_CUDA(h, cudaStreamSynchronize(h->st));
+    return NB_OK;
+}
+
+extern "C" int nb_get_pairs(nb_handle h, int32_t *i, int32_t *j, int64_t cap, int64_t *n)
+{
+    if (!h || !n) return NB_ERR_INVALID;
+    int rc = finish_step(h, nullptr);
+    if (rc && rc != NB_ERR_PAIR_OVERFLOW) return rc;
+    *n = 0;
+    if (!h->stepped || !(h->last_opts & NB_STEP_COLLISIONS)) return NB_OK;
+    NB_CUDA(h, cudaSetDevice(h->device));
+    std::vector<int2> all;
+    for (int r = 0; r < h->nranks; ++r) {
+        unsigned long long c = h->nranks == 1 ? h->h_ctr->n_pairs : h->h_counts[r];
+        c = std::min<unsigned long long>(c, (unsigned long long)h->seg_cap);
+        if (!c) continue;
+        const size_t off = all.size();
+        all.resize(off + c);
+        NB_CUDA(h, cudaMemcpy(all.data() + off, h->d.pairs_all + (long long)r * h->last_params.seg_stride,
+                              c * sizeof(int2), cudaMemcpyDeviceToHost));
+    }
+    std::sort(all.begin(), all.end(), [](const int2 &a, const int2 &b) { return a.x != b.x ? a.x < b.x : a.y < b.y; });
+    *n = (int64_t)all.size();
+    const int64_t m = std::min<int64_t>(cap, *n);
+    for (int64_t k = 0; k < m; ++k) {
+        if (i) i[k] = all[k].x;
+        if (j) j[k] = all[k].y;
+    }
+    return NB_OK;
+}
+
+extern "C" int nb_get_host_events(nb_handle h, nb_event *ev, int64_t cap, int64_t *n)
+{
+    if (!h || !n) return NB_ERR_INVALID;
+    int rc = finish_step(h, nullptr);
+    if (rc && rc != NB_ERR_PAIR_OVERFLOW) return rc;
+    *n = 0;
+    if (!h->stepped) return NB_OK;
+    NB_CUDA(h, cudaSetDevice(h->device));
+    const unsigned long long c = std::min<unsigned long long>(h->h_ctr->n_hev, (unsigned long long)h->hev_cap);
+    std::vector<nb_event> all(c);
+    if (c) NB_CUDA(h, cudaMemcpy(all.data(), h->d.hev, c * sizeof(nb_event), cudaMemcpyDeviceToHost));
+    std::sort(all.begin(), all.end(), [](const nb_event &a, const nb_event &b) {
+        if (a.kind != b.kind) return a.kind < b.kind;
+        if (a.a != b.a) return a.a < b.a;
+        return a.b < b.b;
+    });
+    *n = (int64_t)c;
+    const int64_t m = std::min<int64_t>(cap, *n);
+    if (ev) std::copy(all.begin(), all.begin() + m, ev);
+    return NB_OK;
+}
+
+// ---------------------------------------------------------------- multi-GPU
+extern "C" int nb_comm_unique_id(void *id128)
+{
+    if (!id128) return NB_ERR_INVALID;
+    std::string err;
+    if (!load_nccl(err)) return fail(nullptr, NB_ERR_COMM, err);
+    NcclUid uid;
+    int r = g_nccl.GetUniqueId(&uid);
+    if (r) return fail(nullptr, NB_ERR_COMM, std::string("ncclGetUniqueId: ") + g_nccl.GetErrorString(r));
+    memcpy(id128, &uid, sizeof uid);
+    return NB_OK;
+}
+
+extern "C" int nb_comm_init(nb_handle h, int rank, int nranks, const void *id128)
+{
+    if (!h || !id128 || nranks < 1 || nranks > MAX_RANKS || rank < 0 || rank >= nranks)
+        return fail(h, NB_ERR_INVALID, "nb_comm_init: bad arguments");
+    std::string err;
+    if (!load_nccl(err)) return fail(h, NB_ERR_COMM, err);
+    NB_CUDA(h, cudaSetDevice(h->device));
+    NcclUid uid;
+    memcpy(&uid, id128, sizeof uid);
+    NB_NCCL(h, g_nccl.CommInitRank(&h->comm, nranks, uid, rank));
+    h->rank = rank;
+    h->nranks = nranks;
+    // gathered pair list: one segment per rank
+    if (nranks > 1) {
+        h->d.pairs_all = nullptr;
+        NB_CUDA(h, cudaMalloc((void **)&h->d.pairs_all, (size_t)h->seg_cap * nranks * sizeof(int2)));
+    }
+    return NB_OK;
+}
+
+extern "C" int nb_shard_range(nb_handle h, int64_t *i0, int64_t *i1)
+{
+    if (!h) return NB_ERR_INVALID;
+    const long long shard = (h->n + h->nranks - 1) / h->nranks;
+    const long long a = std::min<long long>(h->n, (long long)h->rank * shard);
+    if (i0) *i0 = a;
+    if (i1) *i1 = std::min<long long>(h->n, a + shard);
+    return NB_OK;
+}
+
+// ---------------------------------------------------------------- diagnostics
+extern "C" int nb_measure_fp64_peak(int device, int iters, double *tflops, float *ms_out)
+{
+    if (!tflops || iters <= 0) return NB_ERR_INVALID;
+    if (cudaSetDevice(device) != cudaSuccess) return fail(nullptr, NB_ERR_NO_DEVICE, "cudaSetDevice failed");
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return NB_ERR_CUDA;
+    const int blocks = prop.multiProcessorCount * 8;
+    double *d_out = nullptr;
+    if (cudaMalloc((void **)&d_out, sizeof(double)) != cudaSuccess) return NB_ERR_CUDA;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    launch_fp64_peak(iters / 8 + 1, blocks, d_out, 0);  // warm-up
+    cudaEventRecord(a, 0);
+    launch_fp64_peak(iters, blocks, d_out, 0);
+    cudaEventRecord(b, 0);
+    cudaError_t e = cudaEventSynchronize(b);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, a, b);
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaFree(d_out);
+    if (e != cudaSuccess) return fail(nullptr, NB_ERR_CUDA, cudaGetErrorString(e));
+    const double fmas = (double)blocks * 256.0 * (double)iters * 16.0 * 8.0;
+    *tflops = 2.0 * fmas / (ms * 1e-3) / 1e12;
+    if (ms_out) *ms_out = ms;
+    return NB_OK;
+}
+
+extern "C" int nb_launch_count(nb_handle h, int64_t *launches)
+{
+    if (!h || !launches) return NB_ERR_INVALID;
+    *launches = h->launches;
+    return NB_OK;
+}

@@ -1,0 +1,225 @@
+// nb_integrate.cu — K4 (integrate + NaN cull + render snapshot) and K5 (stable
+// compaction), plus small utility kernels.
+//
+// K4 restates Body.Update (cmd/body/body.go:114-139) and NewRenderable
+// (cmd/body/renderable.go:22-40); K5 restates the delete half of
+// BodyCollection.Cycle (cmd/body/body_collection.go:253-272).
+// Compiled with -fmad=false so that  v += ts*f/m ; x += ts*v  round exactly like the
+// reference's unfused expressions.
+#include "nb_internal.cuh"
+
+namespace nb {
+
+constexpr int INT_THREADS = 256;
+
+__global__ void __launch_bounds__(INT_THREADS) k_integrate(const __grid_constant__ StepParams p)
+{
+    const DevState &s = p.s;
+    const long long il = (long long)blockIdx.x * INT_THREADS + threadIdx.x;
+    const long long i = p.i0 + il;
+    int culled = 0, dead = 0;
+    const bool apply = !(p.opts & NB_STEP_NO_INTEGRATE) && !s.ctr->overflow;
+    if (i < p.i1) {
+        // partial sums in ascending chunk order, then F = (G*m_i) * sum
+        double sx = 0.0, sy = 0.0, sz = 0.0;
+        for (int c = 0; c < p.n_chunks; ++c) {
+            const long long o = (long long)c * p.n_pad_local + il;
+            sx += s.px[o];
+            sy += s.py[o];
+            sz += s.pz[o];
+        }
+        unsigned fl = s.flags[i];
+        const double m = s.mass[i];
+        const double gm = G_CONST() * m;
+        const bool computes = (fl & NB_F_EXISTS) && !(fl & NB_F_FRAGMENTING);
+        const double fx = computes ? gm * sx : 0.0;
+        const double fy = computes ? gm * sy : 0.0;
+        const double fz = computes ? gm * sz : 0.0;
+        s.fx[i] = fx;
+        s.fy[i] = fy;
+        s.fz[i] = fz;
+        if (apply && (fl & NB_F_EXISTS)) {
+            double vx = s.vx[i], vy = s.vy[i], vz = s.vz[i];
+            if (!(fl & NB_F_COLLIDED) && computes) {
+                vx += p.ts * fx / m;  // body.go:120-122
+                vy += p.ts * fy / m;
+                vz += p.ts * fz / m;
+                s.vx[i] = vx;
+                s.vy[i] = vy;
+                s.vz[i] = vz;
+            }
+            const double x = s.x[i] + p.ts * vx;  // body.go:124-126
+            const double y = s.y[i] + p.ts * vy;
+            const double z = s.z[i] + p.ts * vz;
+            s.x[i] = x;
+            s.y[i] = y;
+            s.z[i] = z;
+            fl &= ~NB_F_COLLIDED;
+            s.rest[i] = p.R;
+            if (isnan(x) || isnan(y) || isnan(z)) {  // body.go:134-137
+                fl &= ~NB_F_EXISTS;
+                culled = 1;
+            }
+            s.flags[i] = (uint8_t)fl;
+        }
+        // NewRenderable
+        const bool ex = (fl & NB_F_EXISTS) != 0;
+        dead = ex ? 0 : 1;
+        s.render_exists[i] = ex ? 1 : 0;
+        s.render[3 * i + 0] = ex ? (float)s.x[i] : 0.0f;
+        s.render[3 * i + 1] = ex ? (float)s.y[i] : 0.0f;
+        s.render[3 * i + 2] = ex ? (float)s.z[i] : 0.0f;
+    }
+    // block-level counts
+    const unsigned cm = __ballot_sync(0xffffffffu, culled), dm = __ballot_sync(0xffffffffu, dead);
+    if ((threadIdx.x & 31) == 0) {
+        if (cm) atomicAdd(&s.ctr->n_culled, (unsigned long long)__popc(cm));
+        if (dm && p.nranks == 1) atomicAdd(&s.ctr->n_dead, (unsigned long long)__popc(dm));
+    }
+}
+
+int launch_integrate(const StepParams &p, cudaStream_t st)
+{
+    const long long n_local = p.i1 - p.i0;
+    if (n_local <= 0) return 0;
+    k_integrate<<<(unsigned)((n_local + INT_THREADS - 1) / INT_THREADS), INT_THREADS, 0, st>>>(p);
+    return 1;
+}
+
+// multi-GPU: after the state exchange every rank counts the dead bodies of the whole array
+__global__ void __launch_bounds__(INT_THREADS) k_count_dead(const __grid_constant__ StepParams p)
+{
+    const long long i = (long long)blockIdx.x * INT_THREADS + threadIdx.x;
+    const int dead = (i < p.n && !(p.s.flags[i] & NB_F_EXISTS)) ? 1 : 0;
+    const unsigned dm = __ballot_sync(0xffffffffu, dead);
+    if ((threadIdx.x & 31) == 0 && dm) atomicAdd(&p.s.ctr->n_dead, (unsigned long long)__popc(dm));
+}
+
+int launch_count_dead(const StepParams &p, cudaStream_t st)
+{
+    if (p.n <= 0) return 0;
+    k_count_dead<<<(unsigned)((p.n + INT_THREADS - 1) / INT_THREADS), INT_THREADS, 0, st>>>(p);
+    return 1;
+}
+
+// ---------------------------------------------------------------- K5: compaction
+constexpr int CP_THREADS = 1024;
+
+// pass 1: live bodies per block
+__global__ void __launch_bounds__(CP_THREADS) k_compact_count(const uint8_t *flags, long long n, unsigned *block_sums)
+{
+    __shared__ unsigned wsum[CP_THREADS / 32];
+    const long long i = (long long)blockIdx.x * CP_THREADS + threadIdx.x;
+    const int live = (i < n && (flags[i] & NB_F_EXISTS)) ? 1 : 0;
+    const unsigned m = __ballot_sync(0xffffffffu, live);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = __popc(m);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned t = 0;
+        for (int w = 0; w < CP_THREADS / 32; ++w) t += wsum[w];
+        block_sums[blockIdx.x] = t;
+    }
+}
+
+// pass 2: exclusive scan of block sums (single CTA, sequential chunks), total → new_n
+__global__ void __launch_bounds__(CP_THREADS) k_compact_scan(unsigned *block_sums, int n_blocks, long long *new_n)
+{
+    __shared__ unsigned warp_tot[CP_THREADS / 32];
+    __shared__ unsigned carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n_blocks; base += CP_THREADS) {
+        const int k = base + threadIdx.x;
+        const unsigned v = k < n_blocks ? block_sums[k] : 0u;
+        unsigned incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((threadIdx.x & 31) >= o) incl += t;
+        }
+        if ((threadIdx.x & 31) == 31) warp_tot[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        unsigned woff = 0;
+        for (int w = 0; w < (threadIdx.x >> 5); ++w) woff += warp_tot[w];
+        const unsigned c = carry;
+        if (k < n_blocks) block_sums[k] = c + woff + incl - v;
+        __syncthreads();
+        if (threadIdx.x == CP_THREADS - 1) carry = c + woff + incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *new_n = (long long)carry;
+}
+
+// pass 3: map[new] = old (stable)
+__global__ void __launch_bounds__(CP_THREADS) k_compact_map(const uint8_t *flags, long long n, const unsigned *block_offs,
+                                                            long long *map)
+{
+    __shared__ unsigned wsum[CP_THREADS / 32];
+    const long long i = (long long)blockIdx.x * CP_THREADS + threadIdx.x;
+    const int live = (i < n && (flags[i] & NB_F_EXISTS)) ? 1 : 0;
+    const unsigned m = __ballot_sync(0xffffffffu, live);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) wsum[w] = __popc(m);
+    __syncthreads();
+    unsigned off = block_offs[blockIdx.x];
+    for (int k = 0; k < w; ++k) off += wsum[k];
+    off += __popc(m & ((1u << lane) - 1u));
+    if (live) map[off] = i;
+}
+
+int launch_compact_map(const DevState &s, long long n, long long *d_map, unsigned *d_block_sums, long long *d_new_n,
+                       cudaStream_t st)
+{
+    if (n <= 0) {
+        cudaMemsetAsync(d_new_n, 0, sizeof(long long), st);
+        return 0;
+    }
+    const int nb = (int)((n + CP_THREADS - 1) / CP_THREADS);
+    k_compact_count<<<nb, CP_THREADS, 0, st>>>(s.flags, n, d_block_sums);
+    k_compact_scan<<<1, CP_THREADS, 0, st>>>(d_block_sums, nb, d_new_n);
+    k_compact_map<<<nb, CP_THREADS, 0, st>>>(s.flags, n, d_block_sums, d_map);
+    return 3;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_gather(const T *src, T *dst, const long long *map, const long long *new_n)
+{
+    const long long k = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (k < *new_n) dst[k] = src[map[k]];
+}
+
+int launch_gather_f64(const double *src, double *dst, const long long *d_map, const long long *d_new_n,
+                      long long n_old, cudaStream_t st)
+{
+    if (n_old <= 0) return 0;
+    k_gather<double><<<(unsigned)((n_old + 255) / 256), 256, 0, st>>>(src, dst, d_map, d_new_n);
+    return 1;
+}
+int launch_gather_u8(const uint8_t *src, uint8_t *dst, const long long *d_map, const long long *d_new_n,
+                     long long n_old, cudaStream_t st)
+{
+    if (n_old <= 0) return 0;
+    k_gather<uint8_t><<<(unsigned)((n_old + 255) / 256), 256, 0, st>>>(src, dst, d_map, d_new_n);
+    return 1;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) k_fill(T *dst, T v, long long n)
+{
+    const long long k = (long long)blockIdx.x * 256 + threadIdx.x;
+    if (k < n) dst[k] = v;
+}
+int launch_fill_f64(double *dst, double v, long long n, cudaStream_t st)
+{
+    if (n <= 0) return 0;
+    k_fill<double><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dst, v, n);
+    return 1;
+}
+int launch_fill_u8(uint8_t *dst, uint8_t v, long long n, cudaStream_t st)
+{
+    if (n <= 0) return 0;
+    k_fill<uint8_t><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(dst, v, n);
+    return 1;
+}
+
+}  // namespace nb

@@ -1,0 +1,91 @@
+// nb_internal.cuh — shared device/host declarations of libnbody_b200.so.
+//
+// Data layout in HBM (all arrays sized to `cap_pad`, a multiple of TJ):
+//   fp64 SoA state   x y z vx vy vz mass radius rest frag_factor frag_step
+//   fp64 derived     jm   (effective j-mass: 0 for !Exists / fragmenting bodies)
+//   fp64 output      fx fy fz
+//   u8               behavior flags
+//   per-tile         tile_rmax[n_tiles]  (max radius of the live bodies of a j-tile)
+//   partial sums     px py pz [S][n_pad_local]  (one slot per j-chunk, summed in
+//                    ascending chunk order by the integrate kernel — the result
+//                    for body i never depends on the grid or the rank count)
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/nbody_b200.h"
+
+namespace nb {
+
+constexpr int TJ = 256;      // bodies per j-tile (one bulk copy of 2 KB per field)
+constexpr int NSTAGE = 2;    // smem stages of the j pipeline
+constexpr int MAX_CHUNKS = 32;  // j-chunks per body (partial-sum slots), function of N only
+constexpr int MAX_RANKS = 16;
+
+// cmd/body/body.go:19
+__host__ __device__ constexpr double G_CONST() { return 6.673e-11; }
+
+struct Counters {
+    unsigned long long n_pairs;     // local pairs appended this step
+    unsigned long long n_hev;       // host events appended this step
+    unsigned long long n_resolved;  // doElastic applications
+    unsigned long long n_culled;    // NaN-culled bodies (local shard)
+    unsigned long long n_dead;      // !Exists bodies after the step (all bodies)
+    int overflow;                   // pair / host-event capacity exceeded
+    int rounds;                     // resolve rounds
+    int total_pairs;                // pairs over all ranks (set by resolve)
+    int _pad;
+};
+
+struct DevState {
+    double *x, *y, *z, *vx, *vy, *vz, *mass, *radius, *rest, *ff, *fs;
+    double *jm;
+    double *fx, *fy, *fz;
+    uint8_t *behavior, *flags;
+    double *tile_rmax;
+    double *px, *py, *pz;
+    float *render;
+    uint8_t *render_exists;
+    int2 *pairs;               // events appended by the local K1 (capacity seg_cap)
+    int2 *pairs_all;           // [nranks][seg_stride] after the exchange (== pairs on one GPU)
+    unsigned long long *pair_counts;  // [nranks] after the exchange
+    nb_event *hev;
+    unsigned long long *head;  // [cap_pad] resolve scheduling keys
+    Counters *ctr;
+};
+
+struct StepParams {
+    DevState s;
+    long long n;         // bodies
+    long long i0, i1;    // local i-shard
+    long long n_pad_local;  // stride of partial-sum slots
+    int n_tiles;         // ceil(n / TJ)
+    int n_chunks;        // S
+    int tiles_per_chunk;
+    int rank, nranks;
+    long long seg_cap;   // pair capacity per rank
+    long long seg_stride;  // stride of the per-rank segments in pairs_all
+    long long hev_cap;
+    unsigned opts;
+    double ts, R;
+};
+
+// launchers (each returns the number of kernel launches it issued)
+int launch_prep(const StepParams &p, cudaStream_t st);
+int launch_force(const StepParams &p, cudaStream_t st, int force_R);
+int launch_resolve(const StepParams &p, cudaStream_t st);
+int launch_integrate(const StepParams &p, cudaStream_t st);
+int launch_count_dead(const StepParams &p, cudaStream_t st);
+// stable compaction of !Exists bodies; returns launches. d_map[k] = old index of new body k.
+int launch_compact_map(const DevState &s, long long n, long long *d_map, unsigned *d_block_sums,
+                       long long *d_new_n, cudaStream_t st);
+int launch_gather_f64(const double *src, double *dst, const long long *d_map, const long long *d_new_n,
+                      long long n_old, cudaStream_t st);
+int launch_gather_u8(const uint8_t *src, uint8_t *dst, const long long *d_map, const long long *d_new_n,
+                     long long n_old, cudaStream_t st);
+int launch_fill_f64(double *dst, double v, long long n, cudaStream_t st);
+int launch_fill_u8(uint8_t *dst, uint8_t v, long long n, cudaStream_t st);
+int launch_fp64_peak(int iters, int blocks, double *d_out, cudaStream_t st);
+
+}  // namespace nb

@@ -1,0 +1,242 @@
+// nb_resolve.cu — K3: deterministic parallel restatement of BodyCollection.ProcessMods
+// for collision events (cmd/body/body_collection.go:212-233 → event.Handle,
+// cmd/body/event.go:53-62 → Body.ResolveCollision, cmd/body/body.go:248-264 →
+// calcElasticCollision / doElastic, cmd/body/collisioncalc.go:26-186, and
+// shouldFragment, cmd/body/fragcalc.go:24-49).
+//
+// Reference semantics (idealised): events are handled serially in
+// reverse arrival order; single-worker arrival order is (i asc, j asc), so the
+// resolve order is descending key = (i << 32 | j).  Two events commute unless they
+// share a body, so the kernel runs rounds: an event is ready when it holds the
+// largest key among the unprocessed events of BOTH its bodies (head[] built with
+// 64-bit atomicMax); ready events of one round touch disjoint bodies and run in
+// parallel.  The outcome equals the serial order exactly, independent of the order
+// in which K1 appended the events.
+//
+// Compiled with -fmad=false: arithmetic is the unfused left-to-right sequence of
+// the reference; only the libm calls (acos/atan2/sin/cos/asin/tan) can differ from
+// Go's / glibc's in the last ulp.
+#include "nb_internal.cuh"
+
+namespace nb {
+
+constexpr int RES_THREADS = 1024;
+constexpr double PI_D = 3.14159265358979323846;
+
+__device__ __forceinline__ bool ef(unsigned b) { return b == NB_ELASTIC || b == NB_FRAGMENT; }
+
+struct CollResult {
+    bool collided;
+    double vx1, vy1, vz1, vx2, vy2, vz2, vx_cm, vy_cm, vz_cm;
+};
+
+// calcElasticCollision, cmd/body/collisioncalc.go:42-186
+__device__ CollResult calc_elastic(const DevState &s, int a, int b)
+{
+    CollResult res;
+    res.collided = false;
+    const double m1 = s.mass[a], m2 = s.mass[b];
+    const double r1 = s.radius[a], r2 = s.radius[b];
+    const double x1 = s.x[a], y1 = s.y[a], z1 = s.z[a];
+    double x2 = s.x[b], y2 = s.y[b], z2 = s.z[b];
+    double vx1 = s.vx[a], vy1 = s.vy[a], vz1 = s.vz[a];
+    const double vx2 = s.vx[b], vy2 = s.vy[b], vz2 = s.vz[b];
+
+    const double r12 = r1 + r2;
+    const double m21 = m2 / m1;
+    const double x21 = x2 - x1, y21 = y2 - y1, z21 = z2 - z1;
+    const double vx21 = vx2 - vx1, vy21 = vy2 - vy1, vz21 = vz2 - vz1;
+
+    const double vx_cm = (m1 * vx1 + m2 * vx2) / (m1 + m2);
+    const double vy_cm = (m1 * vy1 + m2 * vy2) / (m1 + m2);
+    const double vz_cm = (m1 * vz1 + m2 * vz2) / (m1 + m2);
+
+    const double d = sqrt(x21 * x21 + y21 * y21 + z21 * z21);
+    const double v = sqrt(vx21 * vx21 + vy21 * vy21 + vz21 * vz21);
+    if (v == 0) return res;
+
+    x2 = x21; y2 = y21; z2 = z21;
+    vx1 = -vx21; vy1 = -vy21; vz1 = -vz21;
+
+    const double theta2 = acos(z2 / d);
+    const double phi2 = (x2 == 0 && y2 == 0) ? 0.0 : atan2(y2, x2);
+    const double st = sin(theta2), ct = cos(theta2), sp = sin(phi2), cp = cos(phi2);
+
+    double vx1r = ct * cp * vx1 + ct * sp * vy1 - st * vz1;
+    double vy1r = cp * vy1 - sp * vx1;
+    double vz1r = st * cp * vx1 + st * sp * vy1 + ct * vz1;
+    double fvz1r = vz1r / v;
+    if (fvz1r > 1) fvz1r = 1;
+    else if (fvz1r < -1) fvz1r = -1;
+    const double thetav = acos(fvz1r);
+    const double phiv = (vx1r == 0 && vy1r == 0) ? 0.0 : atan2(vy1r, vx1r);
+
+    const double dr = d * sin(thetav) / r12;
+    if (thetav > PI_D / 2 || fabs(dr) > 1) return res;
+
+    const double alpha = asin(-dr);
+    const double beta = phiv;
+    const double sbeta = sin(beta), cbeta = cos(beta);
+    const double a_ = tan(thetav + alpha);
+    const double dvz2 = 2 * (vz1r + a_ * (cbeta * vx1r + sbeta * vy1r)) / ((1 + a_ * a_) * (1 + m21));
+
+    const double vz2r = dvz2;
+    const double vx2r = a_ * cbeta * dvz2;
+    const double vy2r = a_ * sbeta * dvz2;
+    vz1r = vz1r - m21 * vz2r;
+    vx1r = vx1r - m21 * vx2r;
+    vy1r = vy1r - m21 * vy2r;
+
+    res.collided = true;
+    res.vx1 = ct * cp * vx1r - sp * vy1r + st * cp * vz1r + vx2;
+    res.vy1 = ct * sp * vx1r + cp * vy1r + st * sp * vz1r + vy2;
+    res.vz1 = ct * vz1r - st * vx1r + vz2;
+    res.vx2 = ct * cp * vx2r - sp * vy2r + st * cp * vz2r + vx2;
+    res.vy2 = ct * sp * vx2r + cp * vy2r + st * sp * vz2r + vy2;
+    res.vz2 = ct * vz2r - st * vx2r + vz2;
+    res.vx_cm = vx_cm; res.vy_cm = vy_cm; res.vz_cm = vz_cm;
+    return res;
+}
+
+// Body.ResolveCollision for the ready event (a,b); the caller guarantees no other
+// thread touches a or b in this round.
+__device__ void resolve_one(const StepParams &p, int a, int b)
+{
+    const DevState &s = p.s;
+    if (!(s.flags[a] & NB_F_EXISTS) || !(s.flags[b] & NB_F_EXISTS)) return;  // body.go:249-251
+    const unsigned ba = s.behavior[a], bb = s.behavior[b];
+    if (!(ba == NB_ELASTIC && ef(bb))) return;  // body.go:252-253
+    const CollResult r = calc_elastic(s, a, b);
+    if (!r.collided) return;
+    const double br = s.rest[a];
+    const double nvx1 = (r.vx1 - r.vx_cm) * br + r.vx_cm;
+    const double nvy1 = (r.vy1 - r.vy_cm) * br + r.vy_cm;
+    const double nvz1 = (r.vz1 - r.vz_cm) * br + r.vz_cm;
+    const double nvx2 = (r.vx2 - r.vx_cm) * br + r.vx_cm;
+    const double nvy2 = (r.vy2 - r.vy_cm) * br + r.vy_cm;
+    const double nvz2 = (r.vz2 - r.vz_cm) * br + r.vz_cm;
+    if (ba == NB_FRAGMENT || bb == NB_FRAGMENT) {
+        // shouldFragment, fragcalc.go:24-49
+        const double vThis = s.vx[a] + s.vy[a] + s.vz[a];
+        const double dvThis = fabs(s.vx[a] - nvx1) + fabs(s.vy[a] - nvy1) + fabs(s.vz[a] - nvz1);
+        const double thisFactor = dvThis / fabs(vThis);
+        const double vOther = s.vx[b] + s.vy[b] + s.vz[b];
+        const double dvOther = fabs(s.vx[b] - nvx2) + fabs(s.vy[b] - nvy2) + fabs(s.vz[b] - nvz2);
+        const double otherFactor = dvOther / fabs(vOther);
+        if ((ba == NB_FRAGMENT && thisFactor > s.ff[a]) || (bb == NB_FRAGMENT && otherFactor > s.ff[b])) {
+            // doFragment is host work (fragcalc.go:54-117): hand the decision back
+            const unsigned long long k = atomicAdd(&s.ctr->n_hev, 1ull);
+            if (k < (unsigned long long)p.hev_cap) {
+                nb_event e;
+                e.kind = NB_EV_FRAGMENT; e.a = a; e.b = b; e._pad = 0; e.dist = 0; e.f1 = thisFactor; e.f2 = otherFactor;
+                s.hev[k] = e;
+            } else {
+                s.ctr->overflow = 1;
+            }
+            return;
+        }
+    }
+    // doElastic, collisioncalc.go:26-35
+    s.vx[a] = nvx1; s.vy[a] = nvy1; s.vz[a] = nvz1;
+    s.vx[b] = nvx2; s.vy[b] = nvy2; s.vz[b] = nvz2;
+    s.flags[a] |= NB_F_COLLIDED;
+    s.flags[b] |= NB_F_COLLIDED;
+    atomicAdd(&s.ctr->n_resolved, 1ull);
+}
+
+// One CTA. Event e of the concatenated per-rank segments lives at
+// pairs_all[rank*seg_stride + k]; `done` marks are kept by setting pair.x = -1 - x.
+__global__ void __launch_bounds__(RES_THREADS) k_resolve(const __grid_constant__ StepParams p)
+{
+    __shared__ int seg_start[MAX_RANKS + 1];
+    __shared__ int remaining;
+    __shared__ int overflow;
+    const DevState &s = p.s;
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        int acc = 0, ov = s.ctr->overflow;
+        for (int r = 0; r < p.nranks; ++r) {
+            seg_start[r] = acc;
+            const unsigned long long cu = p.nranks == 1 ? s.ctr->n_pairs : s.pair_counts[r];
+            int c = (int)(cu > (unsigned long long)p.seg_cap ? (unsigned long long)p.seg_cap : cu);
+            if (cu > (unsigned long long)p.seg_cap) ov = 1;
+            acc += c;
+        }
+        seg_start[p.nranks] = acc;
+        remaining = acc;
+        overflow = ov;
+        s.ctr->total_pairs = acc;
+        if (ov) s.ctr->overflow = 1;
+    }
+    __syncthreads();
+    const int total = seg_start[p.nranks];
+    if (overflow || (p.opts & (NB_STEP_NO_RESOLVE | NB_STEP_NO_INTEGRATE)) || total == 0) return;
+
+    auto slot = [&](int e) -> long long {
+        int r = 0;
+        while (e >= seg_start[r + 1]) ++r;
+        return (long long)r * p.seg_stride + (e - seg_start[r]);
+    };
+
+    int rounds = 0;
+    while (true) {
+        // 1. publish the largest pending key per body
+        for (int e = tid; e < total; e += RES_THREADS) {
+            const int2 pr = s.pairs_all[slot(e)];
+            if (pr.x < 0) continue;
+            const unsigned long long key = ((unsigned long long)(unsigned)pr.x << 32) | (unsigned)pr.y;
+            atomicMax(&s.head[pr.x], key);
+            atomicMax(&s.head[pr.y], key);
+        }
+        __syncthreads();
+        // 2. an event is ready when it heads both of its bodies
+        //    (ready flag parked in the sign of pair.y)
+        for (int e = tid; e < total; e += RES_THREADS) {
+            const long long sl = slot(e);
+            int2 pr = s.pairs_all[sl];
+            if (pr.x < 0) continue;
+            const unsigned long long key = ((unsigned long long)(unsigned)pr.x << 32) | (unsigned)pr.y;
+            if (__ldcg(&s.head[pr.x]) == key && __ldcg(&s.head[pr.y]) == key) {
+                pr.y = -1 - pr.y;
+                s.pairs_all[sl] = pr;
+            }
+        }
+        __syncthreads();
+        // 3. reset heads, resolve the ready events, mark them done
+        int mine = 0;
+        for (int e = tid; e < total; e += RES_THREADS) {
+            const long long sl = slot(e);
+            int2 pr = s.pairs_all[sl];
+            if (pr.x < 0) continue;
+            const bool ready = pr.y < 0;
+            const int b = ready ? -1 - pr.y : pr.y;
+            s.head[pr.x] = 0ull;
+            s.head[b] = 0ull;
+            if (ready) {
+                resolve_one(p, pr.x, b);
+                s.pairs_all[sl] = make_int2(-1 - pr.x, b);
+                ++mine;
+            }
+        }
+        if (mine) atomicSub(&remaining, mine);
+        ++rounds;
+        __syncthreads();
+        if (remaining <= 0) break;
+        __syncthreads();
+    }
+    // restore the pair list for nb_get_pairs
+    for (int e = tid; e < total; e += RES_THREADS) {
+        const long long sl = slot(e);
+        int2 pr = s.pairs_all[sl];
+        if (pr.x < 0) { pr.x = -1 - pr.x; s.pairs_all[sl] = pr; }
+    }
+    if (tid == 0) s.ctr->rounds = rounds;
+}
+
+int launch_resolve(const StepParams &p, cudaStream_t st)
+{
+    k_resolve<<<1, RES_THREADS, 0, st>>>(p);
+    return 1;
+}
+
+}  // namespace nb

@@ -1,0 +1,51 @@
+"""CPU tests of the drop-in boundary: the library builds for sm_100a, loads, and exports
+every symbol include/nbody_b200.h declares; without a device it fails loudly (no fallback)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from nbodygo_b200 import _build, capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_header_symbols_are_exported():
+    so = _build.build()
+    L = ctypes.CDLL(so)
+    hdr = open(os.path.join(ROOT, "include", "nbody_b200.h")).read()
+    declared = set(re.findall(r"^(?:int|const char \*)\s*\*?(nb_[a-z0-9_]+)\(", hdr, flags=re.M))
+    assert declared == set(capi.SYMBOLS), declared ^ set(capi.SYMBOLS)
+    for sym in declared:
+        assert hasattr(L, sym), sym
+    assert L.nb_abi_version() == 1
+
+
+def test_sm100a_sass_and_tma_present():
+    import subprocess
+    so = _build.build()
+    out = subprocess.run(["cuobjdump", "-lelf", so], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+    sass = subprocess.run(["cuobjdump", "-sass", so], capture_output=True, text=True).stdout
+    assert "UBLKCP" in sass          # 1-D TMA bulk copy of the j-tiles
+    assert "MUFU.RSQ64H" in sass     # fp64 rsqrt seed in the force kernel
+    assert "DFMA" in sass
+
+
+def test_no_cpu_fallback_without_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a device is present")
+    with pytest.raises(capi.NbError) as ei:
+        capi.Sim(16)
+    assert ei.value.code in (capi.NB_ERR_NO_DEVICE, capi.NB_ERR_CUDA)
+
+
+def test_product_package_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "nbodygo_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("the oracle", "").replace("CPU oracle", "") or f == "clouds.py", f

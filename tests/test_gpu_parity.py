@@ -1,0 +1,421 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle.
+
+Bars (north star / SURVEY §7 H3,H5):
+  * collision-pair sets and subsume events: bit-exact (same set, same order after sorting)
+  * forces: |F_gpu - F_exact|_inf <= 1e-12 * sum_j |f_ij|  (normwise; summation order differs)
+  * post-collision velocities: 1e-12 relative to the pair's speed scale (libm last-ulp differences)
+  * integration: bit-exact given identical force/velocity inputs, else the force tolerance propagated
+"""
+import os
+
+import numpy as np
+import pytest
+
+from helpers import load_golden, scene_bodies, scene_step_arrays, unhex
+from nbodygo_b200 import clouds
+from nbodygo_b200.bodies import (ELASTIC, F_COLLIDED, F_EXISTS, F_FRAGMENTING, FRAGMENT, NONE, SUBSUME,
+                                 BodyArrays)
+
+pytestmark = pytest.mark.gpu
+
+FORCE_TOL = 1e-12  # normwise, stated by BASELINE.json north_star
+
+
+@pytest.fixture(scope="module")
+def capi():
+    from nbodygo_b200 import capi as c
+    c.load()
+    return c
+
+
+def oracle_sim(b):
+    from oracle.oracle import OracleSim
+    return OracleSim(b)
+
+
+def assert_forces(fx, fy, fz, o, tol=FORCE_TOL):
+    ex, ey, ez, fn = o.compute_exact()
+    err = np.max(np.abs(np.stack([fx - ex, fy - ey, fz - ez])), axis=0)
+    scale = np.where(fn > 0, fn, 1.0)
+    worst = np.max(err / scale)
+    assert worst <= tol, f"normwise force error {worst:.3e} > {tol}"
+    return worst
+
+
+def run_both(capi, b, ts, R, opts=None, steps=1):
+    """Steps the oracle and the GPU side by side; yields per-step artefacts."""
+    o = oracle_sim(b.copy())
+    sim = capi.Sim(max(b.n, 1))
+    sim.upload(b)
+    out = []
+    for _ in range(steps):
+        o.compute()
+        ref_pairs = o.collision_pairs()
+        ref_events = o.events.copy()
+        ref_forces = (o.fx.copy(), o.fy.copy(), o.fz.copy())
+        o.process_mods()
+        o.update(ts, R)
+        res = sim.step(ts, R, capi.STEP_DEFAULT if opts is None else opts)
+        out.append(dict(res=res, pairs=sim.pairs(), ref_pairs=ref_pairs, ref_events=ref_events,
+                        forces=sim.forces(), ref_forces=ref_forces, hev=sim.host_events(),
+                        state=sim.download(), ref=o.b.copy(), render=sim.render(),
+                        ref_render=(o.render_xyz.copy(), o.render_exists.copy())))
+    sim.close()
+    return out
+
+
+# ---------------------------------------------------------------- golden scenes
+@pytest.mark.parametrize("scene", load_golden(), ids=lambda s: s["name"])
+def test_golden_scene(capi, scene):
+    b = scene_bodies(scene)
+    ts, R = unhex(scene["ts"]), unhex(scene["R"])
+    has_subsume = any(k == "subsume" for st in scene["steps"] for k, *_ in st["events"])
+    sim = capi.Sim(b.n)
+    sim.upload(b)
+    for k, step in enumerate(scene["steps"]):
+        exp = scene_step_arrays(step)
+        res = sim.step(ts, R)
+        live = np.array([r["exists"] for r in scene["init"]]) if k == 0 else prev_exists
+        fx, fy, fz = sim.forces()
+        got_f = np.stack([fx, fy, fz], axis=1)
+        scale = np.max(np.abs(exp["forces"][live])) if live.any() else 1.0
+        assert np.allclose(got_f[live], exp["forces"][live], rtol=1e-12, atol=1e-13 * scale)
+        exp_pairs = [(a, b_) for kind, a, b_, _ in step["events"] if kind == "collision"]
+        assert [tuple(p) for p in sim.pairs()] == sorted(exp_pairs)
+        exp_sub = sorted((a, b_, unhex(d)) for kind, a, b_, d in step["events"] if kind == "subsume")
+        hev = sim.host_events()
+        assert [(int(e["a"]), int(e["b"]), float(e["dist"])) for e in hev if e["kind"] == capi.EV_SUBSUME] == exp_sub
+        got = sim.download()
+        if has_subsume:
+            break  # subsume resolution is host work (ResolveSubsume); the device does not apply it
+        for f in ("x", "y", "z", "vx", "vy", "vz"):
+            a, r = getattr(got, f), exp[f]
+            m = ~np.isnan(r)
+            assert np.array_equal(np.isnan(a), np.isnan(r)), f
+            s = max(np.max(np.abs(r[m])), 1e-300) if m.any() else 1.0
+            assert np.allclose(a[m], r[m], rtol=1e-11, atol=1e-13 * s), f
+        assert np.array_equal(got.exists, exp["exists"])
+        prev_exists = exp["exists"]
+        assert res.n_dead == int((~exp["exists"]).sum())
+    sim.close()
+
+
+def test_kat1_reference_assertion(capi):
+    # cmd/runner/workpool_test.go:41-56 — the reference's own check (Vx != 0), plus the derived bits
+    b = BodyArrays.from_fields([1, 22], [1, 22], [1, 22], [0, 0], [0, 0], [0, 0], [1, 1], [1, 1])
+    sim = capi.Sim(2)
+    sim.upload(b)
+    sim.step(1.0, 1.0)
+    got = sim.download()
+    assert got.vx[0] != 0 and got.vx[1] != 0
+    fx, _, _ = sim.forces()
+    assert abs(fx[0] - 2.912062242103079e-14) <= 4 * np.spacing(2.912062242103079e-14)
+    assert abs(got.x[0] - 1.000000000000029) <= np.spacing(1.0)
+    sim.close()
+
+
+# ---------------------------------------------------------------- random clouds
+@pytest.mark.parametrize("n,seed", [(1, 1), (2, 2), (31, 3), (255, 4), (256, 5), (257, 6), (1000, 7), (4097, 8)])
+def test_cloud_forces_and_pairs(capi, n, seed):
+    b = clouds.uniform_cube(n, 60.0 * max(n, 8) ** (1 / 3), 2.0, 1e15, vmax=10.0, seed=seed)
+    (s,) = run_both(capi, b, 1e-3, 1.0)
+    assert np.array_equal(s["pairs"], s["ref_pairs"])
+    o = oracle_sim(b.copy())
+    assert_forces(*s["forces"], o)
+    assert s["res"].n_pairs == len(s["ref_pairs"])
+
+
+def test_collisions_off_config_c2(capi):
+    # BASELINE config 2 geometry at reduced n: behaviour None ⇒ no events, overlap mask still applies
+    b = clouds.config("C2", n=3000)
+    (s,) = run_both(capi, b, 1e-9, 1.0, opts=0)
+    assert len(s["pairs"]) == 0 and s["res"].n_pairs == 0
+    assert_forces(*s["forces"], oracle_sim(b.copy()))
+    for f in ("x", "vx", "y", "vy"):
+        r = getattr(s["ref"], f)
+        assert np.allclose(getattr(s["state"], f), r, rtol=1e-10, atol=1e-12 * np.max(np.abs(r)))
+
+
+def test_dense_cloud_resolve_matches_serial_order(capi):
+    # many bodies in several collisions at once: the round-based resolve must equal the
+    # reference's serial reverse-arrival order
+    b = clouds.uniform_cube(1500, 60.0, 2.5, 1e12, vmax=100.0, seed=21)
+    (s,) = run_both(capi, b, 1e-4, 0.9)
+    assert len(s["ref_pairs"]) > 1000
+    assert np.array_equal(s["pairs"], s["ref_pairs"])
+    assert s["res"].resolve_rounds > 2
+    vscale = 100.0
+    for f in ("vx", "vy", "vz"):
+        assert np.allclose(getattr(s["state"], f), getattr(s["ref"], f), rtol=0, atol=1e-11 * vscale), f
+    # collided bodies ignore this cycle's force (body.go:118-123) and flags are cleared afterwards
+    assert not (s["state"].flags & F_COLLIDED).any()
+
+
+def test_sim3_like_c1_with_sun_and_subsume(capi):
+    # BASELINE config 1 geometry: sun (Subsume, r=500) + two dense elastic clusters
+    b = clouds.config("C1", n=601)
+    (s,) = run_both(capi, b, 1e-9, 1.0)
+    assert np.array_equal(s["pairs"], s["ref_pairs"])
+    assert len(s["pairs"]) > 100
+    assert_forces(*s["forces"], oracle_sim(b.copy()))
+    for f in ("vx", "vy", "vz"):
+        assert np.allclose(getattr(s["state"], f), getattr(s["ref"], f), rtol=1e-12, atol=1e-4), f
+
+
+def test_subsume_events_are_handed_to_host(capi):
+    from oracle.oracle import EV_SUBSUME
+    rng = np.random.default_rng(3)
+    n = 400
+    b = clouds.uniform_cube(n, 80.0, 1.0, 1e10, vmax=1.0, seed=5)
+    b.radius[:] = rng.uniform(0.5, 6.0, n)
+    b.behavior[rng.random(n) < 0.3] = SUBSUME
+    b.behavior[rng.random(n) < 0.1] = NONE
+    o = oracle_sim(b.copy())
+    o.compute()
+    ref = sorted((int(e["a"]), int(e["b"]), float(e["dist"])) for e in o.events if e["kind"] == EV_SUBSUME)
+    assert len(ref) > 10
+    sim = capi.Sim(n)
+    sim.upload(b)
+    sim.step(1e-6, 1.0)
+    hev = sim.host_events()
+    got = [(int(e["a"]), int(e["b"]), float(e["dist"])) for e in hev if e["kind"] == capi.EV_SUBSUME]
+    assert got == ref
+    assert np.array_equal(sim.pairs(), o.collision_pairs())
+    sim.close()
+
+
+def test_fragment_decisions_are_handed_to_host(capi):
+    from oracle.oracle import EV_FRAGMENT
+    b = clouds.uniform_cube(300, 40.0, 2.0, 1e12, vmax=500.0, seed=13)
+    b.behavior[::3] = FRAGMENT
+    b.frag_factor[:] = 0.05
+    b.frag_step[:] = 100.0
+    o = oracle_sim(b.copy())
+    o.compute()
+    o.process_mods()
+    ref = sorted((int(e["a"]), int(e["b"])) for e in o.host_events if e["kind"] == EV_FRAGMENT)
+    assert len(ref) > 0
+    sim = capi.Sim(b.n)
+    sim.upload(b)
+    sim.step(1e-6, 1.0, capi.STEP_COLLISIONS)
+    hev = sim.host_events()
+    got = sorted((int(e["a"]), int(e["b"])) for e in hev if e["kind"] == capi.EV_FRAGMENT)
+    assert got == ref
+    sim.close()
+
+
+def test_dead_and_fragmenting_bodies(capi):
+    b = clouds.uniform_cube(500, 50.0, 1.5, 1e12, vmax=5.0, seed=17)
+    b.flags[[3, 77, 250]] = 0          # dead: no force from or on them, no events
+    b.mass[[3, 77, 250]] = 0
+    b.flags[[10, 11]] |= F_FRAGMENTING  # skipped as i and as j
+    b.x[77] = np.nan                    # NaN-culled body awaiting compaction
+    (s,) = run_both(capi, b, 1e-3, 1.0)
+    assert np.array_equal(s["pairs"], s["ref_pairs"])
+    fx, fy, fz = s["forces"]
+    live = (b.flags & F_EXISTS != 0) & (b.flags & F_FRAGMENTING == 0)
+    o = oracle_sim(b.copy())
+    ex, ey, ez, fn = o.compute_exact()
+    err = np.abs(fx - ex)[live]
+    assert np.all(err <= FORCE_TOL * fn[live])
+    assert np.all(fx[~live] == 0)
+    assert s["res"].n_dead == 3
+    xyz, ex_flags = s["render"]
+    assert np.array_equal(ex_flags, s["ref_render"][1])
+    assert np.allclose(xyz[ex_flags == 1], s["ref_render"][0][ex_flags == 1], rtol=1e-6)
+    assert np.all(xyz[ex_flags == 0] == 0)
+
+
+def test_mixed_radii_threshold_screen(capi):
+    # a huge body in one tile must not perturb exactness of the screen for the others
+    rng = np.random.default_rng(23)
+    n = 1200
+    b = clouds.uniform_cube(n, 300.0, 1.0, 1e14, vmax=1.0, seed=29)
+    b.radius[:] = rng.uniform(0.1, 8.0, n)
+    b.radius[600] = 120.0
+    b.mass[600] = 1e20
+    (s,) = run_both(capi, b, 1e-5, 1.0)
+    assert np.array_equal(s["pairs"], s["ref_pairs"])
+    assert_forces(*s["forces"], oracle_sim(b.copy()))
+
+
+def test_touching_and_coincident_predicate_edges(capi):
+    # dist == r1+r2 exactly ⇒ collision and no force; one ulp more ⇒ force and no collision;
+    # coincident centres ⇒ collision with NaN velocities ⇒ NaN cull in the same step (KAT-6)
+    b = BodyArrays.from_fields([0, 3, 0, 50, 50], [0, 0, 3.0000000000000004, 50, 50], [0, 0, 0, 50, 50],
+                               [0.5, -0.5, 0, 1, 3], [0, 0, 0, 2, 2], [0, 0, 0, 3, 1],
+                               [1e10] * 5, [1.5, 1.5, 1.5, 2, 2])
+    (s,) = run_both(capi, b, 1e-3, 1.0)
+    assert np.array_equal(s["pairs"], s["ref_pairs"])
+    assert [tuple(p) for p in s["pairs"]] == [(0, 1), (1, 0), (3, 4), (4, 3)]
+    assert np.array_equal(s["state"].exists, s["ref"].exists)
+    assert list(s["state"].exists) == [True, True, True, False, False]
+    assert s["res"].n_culled == 2
+
+
+def test_multi_step_drift(capi):
+    # short trajectory: the documented drift bound is 1e-9 relative to the cloud size over 25 steps
+    b = clouds.uniform_cube(800, 120.0, 1.2, 1e13, vmax=20.0, seed=31)
+    steps = run_both(capi, b, 1e-2, 1.0, steps=25)
+    for k, s in enumerate(steps):
+        assert np.array_equal(s["pairs"], s["ref_pairs"]), f"pair set diverged at step {k}"
+    last = steps[-1]
+    for f in ("x", "y", "z"):
+        assert np.max(np.abs(getattr(last["state"], f) - getattr(last["ref"], f))) <= 1e-9 * 120.0
+    for f in ("vx", "vy", "vz"):
+        assert np.max(np.abs(getattr(last["state"], f) - getattr(last["ref"], f))) <= 1e-9 * 20.0
+
+
+def test_restitution_applies_from_previous_update(capi):
+    # Body.r is set by Update (body.go:129): a new R acts on collisions of the NEXT cycle
+    b = BodyArrays.from_fields([0, 1.9], [0, 0], [0, 0], [1, -1], [0.1, 0], [0, 0.2], [2, 1], [1, 1])
+    steps = run_both(capi, b, 1e-4, 0.5, steps=3)
+    for s in steps:
+        for f in ("vx", "vy", "vz"):
+            assert np.allclose(getattr(s["state"], f), getattr(s["ref"], f), rtol=1e-12, atol=1e-14)
+        assert np.array_equal(s["state"].rest, s["ref"].rest)
+
+
+# ---------------------------------------------------------------- state sync (cycle top)
+def test_empty_collection(capi):
+    sim = capi.Sim(16)
+    sim.upload(BodyArrays(0))
+    res = sim.step(1e-3, 1.0)
+    assert res.n_bodies == 0 and res.n_pairs == 0
+    assert sim.pairs().shape == (0, 2)
+    sim.close()
+
+
+def test_patch_append_compact_semantics(capi):
+    # TestRemove / TestAdds / TestMod semantics (cmd/body/body_collection_test.go:73-88,268-281)
+    n = 1000
+    b = clouds.uniform_cube(n, 400.0, 1.0, 1e12, seed=37)
+    sim = capi.Sim(n + 10)
+    sim.upload(b)
+    # SetNotExists on three bodies (mass 0, exists false)
+    for i in (5, 500, 999):
+        sim.patch(i, 1, mass=np.zeros(1), flags=np.zeros(1, dtype=np.uint8))
+    add = BodyArrays.from_fields([7.0], [8.0], [9.0], [1.0], [2.0], [3.0], [5e11], [2.0])
+    sim.append(add, R=0.75)
+    assert sim.count() == n + 1
+    new_n, old = sim.compact()
+    keep = [i for i in range(n) if i not in (5, 500, 999)] + [n]
+    assert new_n == n - 2 and list(old) == keep
+    got = sim.download()
+    assert np.array_equal(got.x[:-1], b.x[keep[:-1]]) and got.x[-1] == 7.0
+    assert got.rest[-1] == 0.75 and np.all(got.rest[:-1] == 1.0)
+    # ApplyMods: x= and collision=subsume on one body
+    sim.patch(10, 1, x=np.array([41.0]), behavior=np.array([SUBSUME], dtype=np.uint8))
+    got = sim.download()
+    assert got.x[10] == 41.0 and got.behavior[10] == SUBSUME
+    # the stepped state after compaction still matches an oracle fed the same bodies
+    o = oracle_sim(got.copy())
+    o.step(1e-3, 1.0)
+    sim.step(1e-3, 1.0)
+    g2 = sim.download()
+    assert np.allclose(g2.x, o.b.x, rtol=1e-12, atol=1e-9)
+    sim.close()
+
+
+def test_pair_overflow_leaves_state_untouched(capi):
+    b = clouds.uniform_cube(600, 30.0, 2.0, 1e12, vmax=10.0, seed=41)
+    sim = capi.Sim(b.n, pair_capacity=16)
+    sim.upload(b)
+    with pytest.raises(capi.NbError) as ei:
+        sim.step(1e-3, 1.0)
+    assert ei.value.code == capi.NB_ERR_PAIR_OVERFLOW
+    got = sim.download()
+    assert np.array_equal(got.x, b.x) and np.array_equal(got.vx, b.vx)
+    sim.close()
+
+
+def test_capacity_and_argument_errors(capi):
+    sim = capi.Sim(4)
+    with pytest.raises(capi.NbError) as ei:
+        sim.upload(BodyArrays(5))
+    assert ei.value.code == capi.NB_ERR_CAPACITY
+    sim.upload(BodyArrays(4))
+    with pytest.raises(capi.NbError):
+        sim.append(BodyArrays(1), 1.0)
+    with pytest.raises(capi.NbError):
+        sim.patch(3, 2, x=np.zeros(2))
+    sim.close()
+
+
+# ---------------------------------------------------------------- size-independent properties at scale
+def test_register_blocking_does_not_change_bits(capi):
+    # R (i-bodies per thread) is a launch-shape choice; per-body summation order is a function of n only
+    b = clouds.uniform_cube(20_000, 900.0, 1.0, 1e14, vmax=5.0, seed=43)
+    outs = []
+    for R in ("1", "2", "4"):
+        os.environ["NB_FORCE_R"] = R
+        sim = capi.Sim(b.n)
+        sim.upload(b)
+        sim.step(1e-3, 1.0, capi.STEP_COLLISIONS | capi.STEP_NO_INTEGRATE)
+        outs.append((sim.forces(), sim.pairs()))
+        sim.close()
+    os.environ.pop("NB_FORCE_R")
+    for (f, p) in outs[1:]:
+        assert all(np.array_equal(a.view(np.uint64), r.view(np.uint64)) for a, r in zip(f, outs[0][0]))
+        assert np.array_equal(p, outs[0][1])
+
+
+def test_c3_scale_properties_and_sampled_parity(capi):
+    # BASELINE config 3 at full size: 100,000-body cube with elastic collisions
+    b = clouds.config("C3")
+    sim = capi.Sim(b.n)
+    sim.upload(b)
+    res = sim.step(1e-9, 1.0, capi.STEP_COLLISIONS | capi.STEP_NO_INTEGRATE)
+    fx, fy, fz = sim.forces()
+    pairs = sim.pairs()
+    sim.close()
+    # pair set symmetric and free of self pairs
+    assert len(pairs) > 0 and len(pairs) % 2 == 0
+    assert set(map(tuple, pairs)) == set((j, i) for i, j in pairs)
+    assert not np.any(pairs[:, 0] == pairs[:, 1])
+    # Newton's third law, normwise
+    fmag = np.sqrt(fx * fx + fy * fy + fz * fz).sum()
+    assert abs(fx.sum()) + abs(fy.sum()) + abs(fz.sum()) <= 1e-10 * fmag
+    # sampled rows against the oracle: 48 random bodies + every body that collides
+    rng = np.random.default_rng(0)
+    rows = np.unique(np.concatenate([rng.integers(0, b.n, 24), pairs[:16, 0]]))
+    o = oracle_sim(b.copy())
+    ref_pairs = []
+    for i in rows:
+        o.compute(int(i), int(i) + 1)
+        ref_pairs += [tuple(p) for p in o.collision_pairs()]
+        ex, ey, ez, fn = o.compute_exact(int(i), int(i) + 1)
+        err = max(abs(fx[i] - ex[i]), abs(fy[i] - ey[i]), abs(fz[i] - ez[i]))
+        assert err <= FORCE_TOL * fn[i], (i, err / fn[i])
+    rowset = set(rows.tolist())
+    got_rows = [tuple(p) for p in pairs if p[0] in rowset]
+    assert got_rows == sorted(ref_pairs)
+    assert res.n_pairs == len(pairs)
+
+
+def test_c4_full_size_sampled_parity(capi):
+    # BASELINE config 4: 1,000,000-body uniform sphere, elastic; one full step on one GPU,
+    # checked on sampled rows (the oracle cannot do 1e12 pairs) and through global properties
+    b = clouds.config("C4")
+    sim = capi.Sim(b.n)
+    sim.upload(b)
+    res = sim.step(1e-9, 1.0, capi.STEP_COLLISIONS | capi.STEP_NO_INTEGRATE)
+    fx, fy, fz = sim.forces()
+    pairs = sim.pairs()
+    sim.close()
+    assert len(pairs) > 0 and set(map(tuple, pairs)) == set((j, i) for i, j in pairs)
+    fmag = np.sqrt(fx * fx + fy * fy + fz * fz).sum()
+    assert abs(fx.sum()) + abs(fy.sum()) + abs(fz.sum()) <= 1e-9 * fmag
+    rng = np.random.default_rng(1)
+    rows = np.unique(np.concatenate([rng.integers(0, b.n, 3), pairs[:3, 0]]))
+    o = oracle_sim(b.copy())
+    ref_pairs = []
+    for i in rows:
+        o.compute(int(i), int(i) + 1)
+        ref_pairs += [tuple(p) for p in o.collision_pairs()]
+        ex, ey, ez, fn = o.compute_exact(int(i), int(i) + 1)
+        err = max(abs(fx[i] - ex[i]), abs(fy[i] - ey[i]), abs(fz[i] - ez[i]))
+        assert err <= FORCE_TOL * fn[i], (i, err / fn[i])
+    rowset = set(rows.tolist())
+    assert [tuple(p) for p in pairs if p[0] in rowset] == sorted(ref_pairs)
+    assert res.n_pairs == len(pairs)

@@ -277,9 +277,11 @@ __global__ void __launch_bounds__(NT) k_force(const __grid_constant__ StepParams
                                        ri[r], xj, yj, zj, mj);
                     else
                         w = fast_w(d2[r], mj);
-                    ax[r] = __fma_rn(w, dx[r], ax[r]);
-                    ay[r] = __fma_rn(w, dy[r], ay[r]);
-                    az[r] = __fma_rn(w, dz[r], az[r]);
+                    if (w != 0.0) {  // a forceless pair may carry non-finite dx (dead NaN-culled j)
+                        ax[r] = __fma_rn(w, dx[r], ax[r]);
+                        ay[r] = __fma_rn(w, dy[r], ay[r]);
+                        az[r] = __fma_rn(w, dz[r], az[r]);
+                    }
                 }
             } else {
 #pragma unroll

@@ -185,6 +185,13 @@ int nb_comm_init(nb_handle h, int rank, int nranks, const void *id128);
 /* The i-range [i0,i1) this handle computes. */
 int nb_shard_range(nb_handle h, int64_t *i0, int64_t *i1);
 
+/* Pure planning function, usable without a device: the i-range [i0,i1) of `rank`
+ * out of `nranks` for n bodies (contiguous ceil(n/nranks) slices,
+ * computation-runner.go:286-293) and the j-chunking (partial-sum slots per body,
+ * j-tiles of 256 bodies per chunk) — both functions of n only. */
+int nb_plan(int64_t n, int rank, int nranks, int64_t *i0, int64_t *i1, int32_t *n_chunks,
+            int32_t *tiles_per_chunk);
+
 /* ---- diagnostics -------------------------------------------------------- */
 
 /* FP64 FMA throughput of the device: runs `iters` dependent-chain DFMA

@@ -30,7 +30,7 @@ SYMBOLS = (
     "nb_create", "nb_destroy", "nb_last_error", "nb_abi_version", "nb_upload", "nb_patch", "nb_append",
     "nb_compact", "nb_count", "nb_step", "nb_sync", "nb_download_state", "nb_download_render",
     "nb_get_forces", "nb_get_pairs", "nb_get_host_events", "nb_comm_unique_id", "nb_comm_init",
-    "nb_shard_range", "nb_measure_fp64_peak", "nb_launch_count",
+    "nb_shard_range", "nb_plan", "nb_measure_fp64_peak", "nb_launch_count",
 )
 
 
@@ -90,6 +90,7 @@ def load(path: str | None = None):
     L.nb_comm_unique_id.argtypes = [C.c_void_p]
     L.nb_comm_init.argtypes = [H, C.c_int, C.c_int, C.c_void_p]
     L.nb_shard_range.argtypes = [H, _I64P, _I64P]
+    L.nb_plan.argtypes = [C.c_int64, C.c_int, C.c_int, _I64P, _I64P, _I32P, _I32P]
     L.nb_measure_fp64_peak.argtypes = [C.c_int, C.c_int, _DP, C.POINTER(C.c_float)]
     L.nb_launch_count.argtypes = [H, _I64P]
     if path is None:
@@ -241,6 +242,16 @@ class Sim:
         n = C.c_int64(0)
         self._chk(self.L.nb_launch_count(self.h, C.byref(n)))
         return n.value
+
+
+def plan(n: int, rank: int = 0, nranks: int = 1):
+    """(i0, i1, n_chunks, tiles_per_chunk) — pure host arithmetic, no device needed."""
+    L = load()
+    i0, i1, nc, tpc = C.c_int64(0), C.c_int64(0), C.c_int32(0), C.c_int32(0)
+    rc = L.nb_plan(n, rank, nranks, C.byref(i0), C.byref(i1), C.byref(nc), C.byref(tpc))
+    if rc:
+        raise NbError(rc, "nb_plan: bad arguments")
+    return i0.value, i1.value, nc.value, tpc.value
 
 
 def comm_unique_id() -> bytes:

@@ -655,6 +655,22 @@ extern "C" int nb_shard_range(nb_handle h, int64_t *i0, int64_t *i1)
     return NB_OK;
 }
 
+// Pure planning function (no device needed): the i-range of `rank` and the j-chunking for n bodies.
+extern "C" int nb_plan(int64_t n, int rank, int nranks, int64_t *i0, int64_t *i1, int32_t *n_chunks,
+                       int32_t *tiles_per_chunk)
+{
+    if (n < 0 || nranks < 1 || rank < 0 || rank >= nranks) return NB_ERR_INVALID;
+    const long long shard = (n + nranks - 1) / nranks;
+    const long long a = std::min<long long>(n, (long long)rank * shard);
+    if (i0) *i0 = a;
+    if (i1) *i1 = std::min<long long>(n, a + shard);
+    int nt, nc, tpc;
+    chunking(n, nt, nc, tpc);
+    if (n_chunks) *n_chunks = nc;
+    if (tiles_per_chunk) *tiles_per_chunk = tpc;
+    return NB_OK;
+}
+
 // ---------------------------------------------------------------- diagnostics
 extern "C" int nb_measure_fp64_peak(int device, int iters, double *tflops, float *ms_out)
 {

@@ -30,7 +30,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return SO
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc, *NVCC_FLAGS, "-o", SO, *[os.path.join(CSRC, s) for s in SOURCES], "-ldl"]
+    extra = os.environ.get("NB_NVCC_EXTRA", "").split()
+    cmd = [nvcc, *NVCC_FLAGS, *extra, "-o", SO, *[os.path.join(CSRC, s) for s in SOURCES], "-ldl"]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     r = subprocess.run(cmd, capture_output=True, text=True)

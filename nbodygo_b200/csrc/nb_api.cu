@@ -137,6 +137,7 @@ static void free_all(nb_handle h)
     if (h->st) cudaStreamSynchronize(h->st);
     if (h->comm && g_nccl.ok) g_nccl.CommDestroy(h->comm);
     for (int k = 0; k < N_F64; ++k) cudaFree(*f64_fields(h->d, k));
+    cudaFree(h->d.jx); cudaFree(h->d.jy); cudaFree(h->d.jz);
     cudaFree(h->d.jm); cudaFree(h->d.fx); cudaFree(h->d.fy); cudaFree(h->d.fz);
     cudaFree(h->d.behavior); cudaFree(h->d.flags); cudaFree(h->d.tile_rmax);
     cudaFree(h->d.px); cudaFree(h->d.py); cudaFree(h->d.pz);
@@ -188,6 +189,9 @@ extern "C" int nb_create(int device, int64_t capacity, int64_t pair_capacity, nb
         NB_TRY(cudaMalloc((void **)f64_fields(h->d, k), fb));
         NB_TRY(cudaMemsetAsync(*f64_fields(h->d, k), 0, fb, h->st));
     }
+    NB_TRY(cudaMalloc((void **)&h->d.jx, fb));
+    NB_TRY(cudaMalloc((void **)&h->d.jy, fb));
+    NB_TRY(cudaMalloc((void **)&h->d.jz, fb));
     NB_TRY(cudaMalloc((void **)&h->d.jm, fb));
     NB_TRY(cudaMalloc((void **)&h->d.fx, fb));
     NB_TRY(cudaMalloc((void **)&h->d.fy, fb));
@@ -698,6 +702,35 @@ extern "C" int nb_measure_fp64_peak(int device, int iters, double *tflops, float
     const double fmas = (double)blocks * 256.0 * (double)iters * 16.0 * 8.0;
     *tflops = 2.0 * fmas / (ms * 1e-3) / 1e12;
     if (ms_out) *ms_out = ms;
+    return NB_OK;
+}
+
+// Issue-model probe (development diagnostic, see k_fp64_mix): DFMA TFLOP/s with `kind` selecting
+// the number of ALU / MUFU instructions interleaved per 8 DFMA.
+extern "C" int nb_probe_fp64_mix(int device, int kind, int iters, double *tflops)
+{
+    if (!tflops || iters <= 0) return NB_ERR_INVALID;
+    if (cudaSetDevice(device) != cudaSuccess) return NB_ERR_NO_DEVICE;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return NB_ERR_CUDA;
+    const int blocks = prop.multiProcessorCount * 8;
+    double *d_out = nullptr;
+    if (cudaMalloc((void **)&d_out, sizeof(double)) != cudaSuccess) return NB_ERR_CUDA;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    if (!launch_fp64_mix(kind, iters / 8 + 1, blocks, d_out, 0)) { cudaFree(d_out); return NB_ERR_INVALID; }
+    cudaEventRecord(a, 0);
+    launch_fp64_mix(kind, iters, blocks, d_out, 0);
+    cudaEventRecord(b, 0);
+    cudaError_t e = cudaEventSynchronize(b);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, a, b);
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    cudaFree(d_out);
+    if (e != cudaSuccess) return NB_ERR_CUDA;
+    *tflops = 2.0 * (double)blocks * 256.0 * (double)iters * 16.0 * 8.0 / (ms * 1e-3) / 1e12;
     return NB_OK;
 }
 

@@ -5,17 +5,28 @@
 // reference fans out over goroutines (cmd/runner/workpool.go:103-110).
 //
 // K1 layout: one CTA = NT threads x R register-blocked i-bodies, one j-chunk.
-// j-tiles (TJ bodies of x,y,z,jm = 4 x 2 KB) are staged into shared memory with
-// 1-D TMA bulk copies (cp.async.bulk + mbarrier, SASS UBLKCP), double buffered.
-// Per pair the fast path issues 16 FP64-pipe instructions:
+// j-tiles (TJ bodies of jx,jy,jz,jm = 4 x 2 KB) are staged into shared memory with
+// 1-D TMA bulk copies (cp.async.bulk + mbarrier, SASS UBLKCP), double buffered, and
+// read two bodies at a time with broadcast LDS.128.
+//
+// Fast pass (branch-free), per pair 16 FP64-pipe instructions:
 //   3 DADD (dx,dy,dz)  1 DMUL + 2 DFMA (d2)
-//   MUFU.RSQ64H seed (XU pipe)  + 7 DMUL/DFMA (cubic refinement of mj*d^-3)
+//   MUFU.RSQ64H seed (XU pipe) + 7 DMUL/DFMA (cubic refinement of mj*d^-3)
 //   3 DFMA accumulate
-// The overlap predicate of the reference (dist > r_i + r_j, body.go:219) is
-// screened with an integer compare on the high word of d2 against a per-(i,tile)
-// conservative threshold (ALU pipe, no FP64 issue slot); only screened pairs take
-// the exact path, which restates the reference's unfused arithmetic bit for bit
-// (sqrt_rn(fl(fl(dx*dx+dy*dy)+dz*dz)) vs fl(r_i+r_j)) and emits collision events.
+// The overlap predicate of the reference (dist > r_i + r_j, body.go:219) is screened with the
+// running minimum of hi(d2) per (body, tile) against a conservative integer threshold (one
+// VIMNMX3 per two pairs, no branch, no select).  The fast pass is speculative: it accumulates a
+// tile's contribution in per-tile temporaries; if the minimum stayed above the threshold the
+// temporaries are committed, otherwise (rare) the tile is redone for that body: unscreened groups
+// {(i,j),(i,j+1)} with the same fast formula, screened groups through exact_pair, which restates
+// the reference's unfused arithmetic bit for bit (sqrt_rn(fl(fl(dx*dx+dy*dy)+dz*dz)) vs
+// fl(r_i+r_j)) and emits collision events.  Which path a (body, tile) takes depends on the bodies
+// only — never on the launch shape — so results are bit-identical for every R / grid / rank count.
+//
+// Measured issue model on B200 (tools/issue_probe.py): an FP64 instruction holds the
+// SMSP for max(2, #distinct 64-bit register operands) cycles and every other instruction
+// costs about one more, so the loop is written to keep register reads and non-FP64
+// instructions per pair minimal.
 //
 // This file is compiled with -fmad=false: every FMA below is explicit.
 #include "nb_internal.cuh"
@@ -71,40 +82,45 @@ __device__ __forceinline__ double rsqrt_seed(double x)
     return y;
 }
 
-// mj * d2^(-3/2) from the seed y0: with e = 1 - d2*y0^2 (|e| <~ 2^-21),
-// d2^(-3/2) = y0^3 (1-e)^(-3/2) = y0^3 (1 + e(3/2 + 15/8 e) + O(e^3)).  7 FP64 ops.
-__device__ __forceinline__ double fast_w(double d2, double mj)
+// w = mj * d2^(-3/2) from the seed y0: with e = 1 - d2*y0^2 (|e| <~ 2^-21),
+// d2^(-3/2) = y0^3 (1-e)^(-3/2) = y0^3 (1 + e(3/2 + 15/8 e) + O(e^3)).  7 FP64 ops, each reading at
+// most two distinct registers.
+__device__ __forceinline__ double w_from_seed(double y0, double d2, double mj)
 {
-    const double y0 = rsqrt_seed(d2);
     const double u = __dmul_rn(y0, y0);
     const double e = __fma_rn(-d2, u, 1.0);
     const double pp = __fma_rn(1.875, e, 1.5);
+    const double c = __fma_rn(e, pp, 1.0);
     const double t = __dmul_rn(mj, y0);
     const double tu = __dmul_rn(t, u);
-    const double q = __dmul_rn(tu, e);
-    return __fma_rn(q, pp, tu);
+    return __dmul_rn(tu, c);
 }
 
 // ---------------------------------------------------------------- K0: prep
-// jm[j] = Exists && !fragmenting ? mass : 0 (the j-filter of body.go:162-165 folded
-// into the mass), per-tile max radius of live bodies, benign tail beyond n.
+// Builds the j-stream (jx,jy,jz,jm) K1 sweeps: jm = Exists && !fragmenting ? mass : 0 (the
+// j-filter of body.go:162-165 folded into the mass); bodies that do not exist — and the tail of
+// the last tile — are parked massless at a far, finite position so they are never screened.
+// Also the per-tile max radius of live bodies.
 __global__ void __launch_bounds__(TJ) k_prep(StepParams p)
 {
     const long long j = (long long)blockIdx.x * TJ + threadIdx.x;
-    double r = 0.0;
+    double r = 0.0, x = 1e150, y = 1e150, z = 1e150, m = 0.0;
     if (j < p.n) {
         const unsigned fl = p.s.flags[j];
-        const bool live = (fl & NB_F_EXISTS) != 0;
-        const bool src = live && !(fl & NB_F_FRAGMENTING);
-        p.s.jm[j] = src ? p.s.mass[j] : 0.0;
-        if (live) r = p.s.radius[j];
-    } else {
-        // tail of the last tile: massless, far away, finite
-        p.s.x[j] = 1e150;
-        p.s.y[j] = 1e150;
-        p.s.z[j] = 1e150;
-        p.s.jm[j] = 0.0;
+        const double px = p.s.x[j], py = p.s.y[j], pz = p.s.z[j];
+        // a live body at a non-finite position is inert as a j-body (the reference would poison
+        // every force with NaN); as an i-body it still receives NaN and is culled by K4
+        const bool live = (fl & NB_F_EXISTS) != 0 && isfinite(px) && isfinite(py) && isfinite(pz);
+        if (live) {
+            x = px; y = py; z = pz;
+            r = p.s.radius[j];
+            if (!(fl & NB_F_FRAGMENTING)) m = p.s.mass[j];
+        }
     }
+    p.s.jx[j] = x;
+    p.s.jy[j] = y;
+    p.s.jz[j] = z;
+    p.s.jm[j] = m;
     // block max of r (NaN radii are ignored by fmax)
     __shared__ double red[TJ / 32];
 #pragma unroll
@@ -112,10 +128,10 @@ __global__ void __launch_bounds__(TJ) k_prep(StepParams p)
     if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = r;
     __syncthreads();
     if (threadIdx.x == 0) {
-        double m = red[0];
+        double mx = red[0];
 #pragma unroll
-        for (int w = 1; w < TJ / 32; ++w) m = fmax(m, red[w]);
-        p.s.tile_rmax[blockIdx.x] = m;
+        for (int w = 1; w < TJ / 32; ++w) mx = fmax(mx, red[w]);
+        p.s.tile_rmax[blockIdx.x] = mx;
     }
 }
 
@@ -151,8 +167,6 @@ __device__ __noinline__ void emit_event(const StepParams &p, long long i, long l
                 nb_event e;
                 e.kind = NB_EV_SUBSUME; e.a = a; e.b = b; e._pad = 0; e.dist = dist; e.f1 = 0; e.f2 = 0;
                 p.s.hev[k] = e;
-            } else {
-                p.s.ctr->overflow = 1;
             }
         }
     }
@@ -181,9 +195,11 @@ __device__ __noinline__ double exact_pair(const StepParams &p, long long i, long
 }
 
 // ---------------------------------------------------------------- K1: kernel
-template <int R, int NT>
-__global__ void __launch_bounds__(NT) k_force(const __grid_constant__ StepParams p)
+// UNR = unroll of the j-group loop (each group is two j-bodies).
+template <int R, int NT, int MINB, int UNR>
+__global__ void __launch_bounds__(NT, MINB) k_force(const __grid_constant__ StepParams p)
 {
+    static_assert(TJ % 2 == 0 && R <= 16, "tile of j-pairs");
     __shared__ __align__(128) double sm[NSTAGE][4][TJ];
     __shared__ __align__(8) uint64_t bar[NSTAGE];
 
@@ -202,13 +218,13 @@ __global__ void __launch_bounds__(NT) k_force(const __grid_constant__ StepParams
     }
     __syncthreads();
 
-    auto issue = [&](int t) {  // thread 0 only: stage tile t0+t
+    auto issue = [&](int t) {  // thread 0 only: stage tile t0+t of the j-stream
         const int s = t % NSTAGE;
         const long long j0 = (long long)(t0 + t) * TJ;
         mbar_expect_tx(&bar[s], 4u * TJ * sizeof(double));
-        bulk_g2s(&sm[s][0][0], p.s.x + j0, TJ * sizeof(double), &bar[s]);
-        bulk_g2s(&sm[s][1][0], p.s.y + j0, TJ * sizeof(double), &bar[s]);
-        bulk_g2s(&sm[s][2][0], p.s.z + j0, TJ * sizeof(double), &bar[s]);
+        bulk_g2s(&sm[s][0][0], p.s.jx + j0, TJ * sizeof(double), &bar[s]);
+        bulk_g2s(&sm[s][1][0], p.s.jy + j0, TJ * sizeof(double), &bar[s]);
+        bulk_g2s(&sm[s][2][0], p.s.jz + j0, TJ * sizeof(double), &bar[s]);
         bulk_g2s(&sm[s][3][0], p.s.jm + j0, TJ * sizeof(double), &bar[s]);
     };
     if (tid == 0) {
@@ -235,63 +251,95 @@ __global__ void __launch_bounds__(NT) k_force(const __grid_constant__ StepParams
         const int s = t % NSTAGE;
         if (tid == 0 && t + NSTAGE - 1 < nt) issue(t + NSTAGE - 1);
 
-        // conservative screen for this tile: not screened  <=>  thr+1 <= hi(d2) < 0x7FF00000
-        unsigned thrp1[R], lim[R];
+        // Conservative per-body screen for this tile: a pair (i,j) can only overlap (or be
+        // degenerate) if hi(d2) < thr_i, thr_i = hi((r_i + rmax_tile)^2 (1+2^-18)) + 2.
+        unsigned thr[R], lo[R];
+        double tx[R], ty[R], tz[R];  // this tile's contribution, committed only if nothing was screened
         const double rm = p.s.tile_rmax[t0 + t];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-            unsigned thr = 0;
+            thr[r] = 0u;
+            lo[r] = 0xFFFFFFFFu;
+            tx[r] = ty[r] = tz[r] = 0.0;
             if (alive[r]) {
                 const double sr = __dadd_rn(ri[r], rm);
                 const double t2 = __dmul_rn(__dmul_rn(sr, sr), 1.0 + 1.0 / 262144.0);
-                thr = (unsigned)__double2hiint(t2) + 1u;
-                if (thr > 0x7FEFFFFFu) thr = 0x7FEFFFFFu;
+                unsigned v = (unsigned)__double2hiint(t2) + 2u;
+                if (v > 0x7FF00000u) v = 0x7FF00000u;  // inf / NaN radii: screen every finite pair
+                thr[r] = v;
             }
-            thrp1[r] = thr + 1u;
-            lim[r] = 0x7FF00000u - thrp1[r];
         }
 
         mbar_wait(&bar[s], (unsigned)((t / NSTAGE) & 1));
         const double *sx = sm[s][0], *sy = sm[s][1], *sz = sm[s][2], *sj = sm[s][3];
         const long long jt0 = (long long)(t0 + t) * TJ;
 
-#pragma unroll 2
-        for (int jj = 0; jj < TJ; ++jj) {
-            const double xj = sx[jj], yj = sy[jj], zj = sz[jj], mj = sj[jj];
-            double dx[R], dy[R], dz[R], d2[R];
-            bool screened = false;
+        // ---- fast pass: branch-free and unmasked (speculative); only the running minimum of
+        //      hi(d2) is kept per body
+#pragma unroll(UNR)
+        for (int jj = 0; jj < TJ; jj += 2) {
+            const double2 vx = *reinterpret_cast<const double2 *>(sx + jj);
+            const double2 vy = *reinterpret_cast<const double2 *>(sy + jj);
+            const double2 vz = *reinterpret_cast<const double2 *>(sz + jj);
+            const double2 vm = *reinterpret_cast<const double2 *>(sj + jj);
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                dx[r] = __dsub_rn(xj, xi[r]);
-                dy[r] = __dsub_rn(yj, yi[r]);
-                dz[r] = __dsub_rn(zj, zi[r]);
-                d2[r] = __fma_rn(dz[r], dz[r], __fma_rn(dy[r], dy[r], __dmul_rn(dx[r], dx[r])));
-                screened |= ((unsigned)__double2hiint(d2[r]) - thrp1[r]) >= lim[r];
+                const double dxa = __dsub_rn(vx.x, xi[r]), dxb = __dsub_rn(vx.y, xi[r]);
+                const double dya = __dsub_rn(vy.x, yi[r]), dyb = __dsub_rn(vy.y, yi[r]);
+                const double dza = __dsub_rn(vz.x, zi[r]), dzb = __dsub_rn(vz.y, zi[r]);
+                const double d2a = __fma_rn(dza, dza, __fma_rn(dya, dya, __dmul_rn(dxa, dxa)));
+                const double d2b = __fma_rn(dzb, dzb, __fma_rn(dyb, dyb, __dmul_rn(dxb, dxb)));
+                lo[r] = min(lo[r], min((unsigned)__double2hiint(d2a), (unsigned)__double2hiint(d2b)));
+                const double wa = w_from_seed(rsqrt_seed(d2a), d2a, vm.x);
+                const double wb = w_from_seed(rsqrt_seed(d2b), d2b, vm.y);
+                tx[r] = __fma_rn(wa, dxa, tx[r]);
+                ty[r] = __fma_rn(wa, dya, ty[r]);
+                tz[r] = __fma_rn(wa, dza, tz[r]);
+                tx[r] = __fma_rn(wb, dxb, tx[r]);
+                ty[r] = __fma_rn(wb, dyb, ty[r]);
+                tz[r] = __fma_rn(wb, dzb, tz[r]);
             }
-            if (__any_sync(0xffffffffu, screened)) {
+        }
+
+        // ---- commit, or (rare) redo the tile carefully for a body that saw a screened pair.
+        //      The redo follows the same j order: unscreened groups {j,j+1} with the fast formula,
+        //      screened groups through exact_pair.  Which path a body takes depends on (i, tile) only.
 #pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    double w;
-                    if (((unsigned)__double2hiint(d2[r]) - thrp1[r]) >= lim[r])
-                        w = exact_pair(p, ibase + (long long)r * NT + tid, jt0 + jj, alive[r], xi[r], yi[r], zi[r],
-                                       ri[r], xj, yj, zj, mj);
-                    else
-                        w = fast_w(d2[r], mj);
-                    if (w != 0.0) {  // a forceless pair may carry non-finite dx (dead NaN-culled j)
-                        ax[r] = __fma_rn(w, dx[r], ax[r]);
-                        ay[r] = __fma_rn(w, dy[r], ay[r]);
-                        az[r] = __fma_rn(w, dz[r], az[r]);
+        for (int r = 0; r < R; ++r) {
+            if (lo[r] < thr[r]) {
+                double cx = 0.0, cy = 0.0, cz = 0.0;
+#pragma unroll 1
+                for (int jj = 0; jj < TJ; jj += 2) {
+                    double dx[2], dy[2], dz[2], d2[2];
+#pragma unroll
+                    for (int g = 0; g < 2; ++g) {
+                        dx[g] = __dsub_rn(sx[jj + g], xi[r]);
+                        dy[g] = __dsub_rn(sy[jj + g], yi[r]);
+                        dz[g] = __dsub_rn(sz[jj + g], zi[r]);
+                        d2[g] = __fma_rn(dz[g], dz[g], __fma_rn(dy[g], dy[g], __dmul_rn(dx[g], dx[g])));
+                    }
+                    const bool screened =
+                        min((unsigned)__double2hiint(d2[0]), (unsigned)__double2hiint(d2[1])) < thr[r];
+#pragma unroll
+                    for (int g = 0; g < 2; ++g) {
+                        double w;
+                        if (screened)
+                            w = exact_pair(p, ibase + (long long)r * NT + tid, jt0 + jj + g, alive[r], xi[r], yi[r],
+                                           zi[r], ri[r], sx[jj + g], sy[jj + g], sz[jj + g], sj[jj + g]);
+                        else
+                            w = w_from_seed(rsqrt_seed(d2[g]), d2[g], sj[jj + g]);
+                        if (w != 0.0) {
+                            cx = __fma_rn(w, dx[g], cx);
+                            cy = __fma_rn(w, dy[g], cy);
+                            cz = __fma_rn(w, dz[g], cz);
+                        }
                     }
                 }
-            } else {
-#pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    const double w = fast_w(d2[r], mj);
-                    ax[r] = __fma_rn(w, dx[r], ax[r]);
-                    ay[r] = __fma_rn(w, dy[r], ay[r]);
-                    az[r] = __fma_rn(w, dz[r], az[r]);
-                }
+                tx[r] = cx; ty[r] = cy; tz[r] = cz;
             }
+            ax[r] = __dadd_rn(ax[r], tx[r]);
+            ay[r] = __dadd_rn(ay[r], ty[r]);
+            az[r] = __dadd_rn(az[r], tz[r]);
         }
         __syncthreads();  // every warp is done with stage s before it is refilled
     }
@@ -309,18 +357,18 @@ __global__ void __launch_bounds__(NT) k_force(const __grid_constant__ StepParams
     }
 }
 
-template <int R, int NT>
+template <int R, int NT, int MINB, int UNR>
 static int launch_force_t(const StepParams &p, cudaStream_t st)
 {
     const long long n_local = p.i1 - p.i0;
     const long long per = (long long)NT * R;
     dim3 grid((unsigned)((n_local + per - 1) / per), (unsigned)p.n_chunks);
-    k_force<R, NT><<<grid, NT, 0, st>>>(p);
+    k_force<R, NT, MINB, UNR><<<grid, NT, 0, st>>>(p);
     return 1;
 }
 
 // R is chosen from the local shard size only; it never changes the result bits
-// (each body's j-order and chunking are functions of n alone).
+// (each body's j-order, chunking and screening are functions of the bodies alone).
 int launch_force(const StepParams &p, cudaStream_t st, int force_R)
 {
     const long long n_local = p.i1 - p.i0;
@@ -333,10 +381,20 @@ int launch_force(const StepParams &p, cudaStream_t st, int force_R)
         else if (ctas2 >= 148 * 4 * 2) R = 2;
         else R = 1;
     }
+    // Values above 9 (NB_FORCE_R) select alternative launch shapes for tools/kbench.py:
+    // 1000*UNR + 100*MINB + 10*(NT==256) + R.  Production shapes: R in {4,2,1}, NT 128, UNR 2.
     switch (R) {
-        case 4: return launch_force_t<4, 128>(p, st);
-        case 2: return launch_force_t<2, 128>(p, st);
-        default: return launch_force_t<1, 128>(p, st);
+        case 4: return launch_force_t<4, 128, 1, 2>(p, st);
+        case 2: return launch_force_t<2, 128, 1, 2>(p, st);
+        case 1: return launch_force_t<1, 128, 1, 2>(p, st);
+        case 3: return launch_force_t<3, 128, 1, 2>(p, st);
+        case 1004: return launch_force_t<4, 128, 1, 1>(p, st);
+        case 1002: return launch_force_t<2, 128, 1, 1>(p, st);
+        case 4004: return launch_force_t<4, 128, 1, 4>(p, st);
+        case 2014: return launch_force_t<4, 256, 1, 2>(p, st);
+        case 2012: return launch_force_t<2, 256, 1, 2>(p, st);
+        case 2006: return launch_force_t<6, 128, 1, 2>(p, st);
+        default: return launch_force_t<1, 128, 1, 2>(p, st);
     }
 }
 
@@ -360,6 +418,75 @@ __global__ void __launch_bounds__(256) k_fp64_peak(int iters, double *out)
 int launch_fp64_peak(int iters, int blocks, double *d_out, cudaStream_t st)
 {
     k_fp64_peak<<<blocks, 256, 0, st>>>(iters, d_out);
+    return 1;
+}
+
+// ---------------------------------------------------------------- issue-model probes
+// 8 independent DFMA chains with NI integer (ALU) op pairs and NM MUFU.RSQ64H per 8 DFMA.
+template <int NI, int NM>
+__global__ void __launch_bounds__(256) k_fp64_mix(int iters, double *out)
+{
+    double a0 = 1.0 + threadIdx.x * 1e-9, a1 = a0 + 1e-3, a2 = a0 + 2e-3, a3 = a0 + 3e-3;
+    double a4 = a0 + 4e-3, a5 = a0 + 5e-3, a6 = a0 + 6e-3, a7 = a0 + 7e-3;
+    const double m = 0.999999999, c = 1e-9;
+    unsigned x0 = threadIdx.x, x1 = blockIdx.x, x2 = 7u, x3 = 11u;
+    double q = 1.0 + threadIdx.x;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            a0 = __fma_rn(a0, m, c); a1 = __fma_rn(a1, m, c); a2 = __fma_rn(a2, m, c); a3 = __fma_rn(a3, m, c);
+            a4 = __fma_rn(a4, m, c); a5 = __fma_rn(a5, m, c); a6 = __fma_rn(a6, m, c); a7 = __fma_rn(a7, m, c);
+#pragma unroll
+            for (int i = 0; i < NI; ++i) {
+                if ((i & 3) == 0) x0 = __funnelshift_l(x0, x0, 3) ^ x1;
+                if ((i & 3) == 1) x1 = __funnelshift_l(x1, x1, 5) ^ x2;
+                if ((i & 3) == 2) x2 = __funnelshift_l(x2, x2, 7) ^ x3;
+                if ((i & 3) == 3) x3 = __funnelshift_l(x3, x3, 9) ^ x0;
+            }
+#pragma unroll
+            for (int i = 0; i < NM; ++i) q = rsqrt_seed(q + 1.5);
+        }
+    }
+    const double s = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7 + q;
+    if (s == 123.456 || (x0 ^ x1 ^ x2 ^ x3) == 0x12345u) out[0] = s;
+}
+
+// every DFMA reads three distinct register pairs (no operand reuse)
+__global__ void __launch_bounds__(256) k_fp64_rf(int iters, double *out)
+{
+    double a[8], b[8], c[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        a[k] = 1.0 + threadIdx.x * 1e-9 + k * 1e-3;
+        b[k] = 0.999999 + k * 1e-9 + threadIdx.x * 1e-12;
+        c[k] = 1e-9 * (k + 1) + threadIdx.x * 1e-15;
+    }
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) a[k] = __fma_rn(b[k], c[(k + u) & 7], a[k]);
+        }
+    }
+    double s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += a[k];
+    if (s == 123.456) out[0] = s;
+}
+
+int launch_fp64_mix(int kind, int iters, int blocks, double *d_out, cudaStream_t st)
+{
+    switch (kind) {
+        case 0: k_fp64_mix<0, 0><<<blocks, 256, 0, st>>>(iters, d_out); break;
+        case 1: k_fp64_mix<2, 0><<<blocks, 256, 0, st>>>(iters, d_out); break;
+        case 2: k_fp64_mix<4, 0><<<blocks, 256, 0, st>>>(iters, d_out); break;
+        case 3: k_fp64_mix<8, 0><<<blocks, 256, 0, st>>>(iters, d_out); break;
+        case 4: k_fp64_mix<16, 0><<<blocks, 256, 0, st>>>(iters, d_out); break;
+        case 5: k_fp64_mix<0, 1><<<blocks, 256, 0, st>>>(iters, d_out); break;
+        case 6: k_fp64_mix<4, 1><<<blocks, 256, 0, st>>>(iters, d_out); break;
+        case 7: k_fp64_rf<<<blocks, 256, 0, st>>>(iters, d_out); break;
+        default: return 0;
+    }
     return 1;
 }
 

@@ -40,7 +40,7 @@ struct Counters {
 
 struct DevState {
     double *x, *y, *z, *vx, *vy, *vz, *mass, *radius, *rest, *ff, *fs;
-    double *jm;
+    double *jx, *jy, *jz, *jm;  // j-stream built by K0 (sanitised positions + effective mass)
     double *fx, *fy, *fz;
     uint8_t *behavior, *flags;
     double *tile_rmax;
@@ -87,5 +87,6 @@ int launch_gather_u8(const uint8_t *src, uint8_t *dst, const long long *d_map, c
 int launch_fill_f64(double *dst, double v, long long n, cudaStream_t st);
 int launch_fill_u8(uint8_t *dst, uint8_t v, long long n, cudaStream_t st);
 int launch_fp64_peak(int iters, int blocks, double *d_out, cudaStream_t st);
+int launch_fp64_mix(int kind, int iters, int blocks, double *d_out, cudaStream_t st);
 
 }  // namespace nb

@@ -143,7 +143,7 @@ static void free_all(nb_handle h)
     cudaFree(h->d.px); cudaFree(h->d.py); cudaFree(h->d.pz);
     cudaFree(h->d.render); cudaFree(h->d.render_exists);
     if (h->d.pairs_all != h->d.pairs) cudaFree(h->d.pairs_all);
-    cudaFree(h->d.pairs); cudaFree(h->d.hev); cudaFree(h->d.head); cudaFree(h->d.ctr);
+    cudaFree(h->d.pairs); cudaFree(h->d.hev); cudaFree(h->d.head); cudaFree(h->d.ctr); cudaFree(h->d.zeros);
     cudaFree(h->scratch_f64); cudaFree(h->scratch_u8); cudaFree(h->d_map); cudaFree(h->d_new_n);
     cudaFree(h->d_block_sums); cudaFree(h->d_pair_counts);
     if (h->h_ctr) cudaFreeHost(h->h_ctr);
@@ -212,6 +212,8 @@ extern "C" int nb_create(int device, int64_t capacity, int64_t pair_capacity, nb
     NB_TRY(cudaMalloc((void **)&h->d.hev, (size_t)h->hev_cap * sizeof(nb_event)));
     NB_TRY(cudaMalloc((void **)&h->d.head, (size_t)h->cap_pad * sizeof(unsigned long long)));
     NB_TRY(cudaMemsetAsync(h->d.head, 0, (size_t)h->cap_pad * sizeof(unsigned long long), h->st));
+    NB_TRY(cudaMalloc((void **)&h->d.zeros, 1024 * sizeof(unsigned)));
+    NB_TRY(cudaMemsetAsync(h->d.zeros, 0, 1024 * sizeof(unsigned), h->st));
     NB_TRY(cudaMalloc((void **)&h->d.ctr, sizeof(Counters)));
     NB_TRY(cudaMemsetAsync(h->d.ctr, 0, sizeof(Counters), h->st));
     NB_TRY(cudaMalloc((void **)&h->scratch_f64, fb));

@@ -82,6 +82,26 @@ __device__ __forceinline__ double rsqrt_seed(double x)
     return y;
 }
 
+// Seed whose low word is `lo` instead of the canonical 0.  MUFU.RSQ64H writes only the high word;
+// the low word of the seed is irrelevant to the result's accuracy (it perturbs y0 by < 2^-20, and
+// the cubic refinement absorbs e up to ~2^-19 with an O(e^3) ~ 1e-17 residue), so pairing the MUFU
+// result with a long-lived register spares one MOV per pair.  `lo` is always 0 at run time (an
+// opaque zero, so the compiler cannot rematerialise it) which keeps results reproducible.
+__device__ __forceinline__ double rsqrt_seed_lo(double x, unsigned lo)
+{
+    double y;
+    asm("{\n"
+        ".reg .b32 tl, th;\n"
+        ".reg .f64 t;\n"
+        "rsqrt.approx.ftz.f64 t, %1;\n"
+        "mov.b64 {tl, th}, t;\n"
+        "mov.b64 %0, {%2, th};\n"
+        "}\n"
+        : "=d"(y)
+        : "d"(x), "r"(lo));
+    return y;
+}
+
 // w = mj * d2^(-3/2) from the seed y0: with e = 1 - d2*y0^2 (|e| <~ 2^-21),
 // d2^(-3/2) = y0^3 (1-e)^(-3/2) = y0^3 (1 + e(3/2 + 15/8 e) + O(e^3)).  7 FP64 ops, each reading at
 // most two distinct registers.
@@ -234,6 +254,9 @@ __global__ void __launch_bounds__(NT, MINB) k_force(const __grid_constant__ Step
     double xi[R], yi[R], zi[R], ri[R];
     double ax[R], ay[R], az[R];
     bool alive[R];
+    unsigned zlo[2 * R];  // opaque zeros: low words of the rsqrt seeds (see rsqrt_seed_lo)
+#pragma unroll
+    for (int k = 0; k < 2 * R; ++k) zlo[k] = __ldcg(&p.s.zeros[(tid + 32 * k) & 1023]);
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         const long long i = ibase + (long long)r * NT + tid;
@@ -290,8 +313,8 @@ __global__ void __launch_bounds__(NT, MINB) k_force(const __grid_constant__ Step
                 const double d2a = __fma_rn(dza, dza, __fma_rn(dya, dya, __dmul_rn(dxa, dxa)));
                 const double d2b = __fma_rn(dzb, dzb, __fma_rn(dyb, dyb, __dmul_rn(dxb, dxb)));
                 lo[r] = min(lo[r], min((unsigned)__double2hiint(d2a), (unsigned)__double2hiint(d2b)));
-                const double wa = w_from_seed(rsqrt_seed(d2a), d2a, vm.x);
-                const double wb = w_from_seed(rsqrt_seed(d2b), d2b, vm.y);
+                const double wa = w_from_seed(rsqrt_seed_lo(d2a, zlo[2 * r]), d2a, vm.x);
+                const double wb = w_from_seed(rsqrt_seed_lo(d2b, zlo[2 * r + 1]), d2b, vm.y);
                 tx[r] = __fma_rn(wa, dxa, tx[r]);
                 ty[r] = __fma_rn(wa, dya, ty[r]);
                 tz[r] = __fma_rn(wa, dza, tz[r]);
@@ -382,18 +405,16 @@ int launch_force(const StepParams &p, cudaStream_t st, int force_R)
         else R = 1;
     }
     // Values above 9 (NB_FORCE_R) select alternative launch shapes for tools/kbench.py:
-    // 1000*UNR + 100*MINB + 10*(NT==256) + R.  Production shapes: R in {4,2,1}, NT 128, UNR 2.
+    // 1000*UNR + 100*MINB + 10*(NT==256) + R.  Production shapes: R in {4,2,1}, NT 128.
     switch (R) {
-        case 4: return launch_force_t<4, 128, 1, 2>(p, st);
-        case 2: return launch_force_t<2, 128, 1, 2>(p, st);
+        case 4: return launch_force_t<4, 128, 1, 1>(p, st);
+        case 2: return launch_force_t<2, 128, 1, 1>(p, st);
         case 1: return launch_force_t<1, 128, 1, 2>(p, st);
-        case 3: return launch_force_t<3, 128, 1, 2>(p, st);
-        case 1004: return launch_force_t<4, 128, 1, 1>(p, st);
-        case 1002: return launch_force_t<2, 128, 1, 1>(p, st);
-        case 4004: return launch_force_t<4, 128, 1, 4>(p, st);
+        case 3: return launch_force_t<3, 128, 1, 1>(p, st);
+        case 2004: return launch_force_t<4, 128, 1, 2>(p, st);
+        case 2002: return launch_force_t<2, 128, 1, 2>(p, st);
         case 2014: return launch_force_t<4, 256, 1, 2>(p, st);
-        case 2012: return launch_force_t<2, 256, 1, 2>(p, st);
-        case 2006: return launch_force_t<6, 128, 1, 2>(p, st);
+        case 1012: return launch_force_t<2, 256, 1, 1>(p, st);
         default: return launch_force_t<1, 128, 1, 2>(p, st);
     }
 }

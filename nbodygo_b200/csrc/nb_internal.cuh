@@ -53,6 +53,7 @@ struct DevState {
     nb_event *hev;
     unsigned long long *head;  // [cap_pad] resolve scheduling keys
     Counters *ctr;
+    unsigned *zeros;           // 1024 zeros (opaque low words for the rsqrt seeds in K1)
 };
 
 struct StepParams {

@@ -1,0 +1,328 @@
+// host_runner.cc — GpuStepper (the C++ twin of the cgo shim) and ComputationRunner.
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <stdexcept>
+
+#include "nbody_host.h"
+
+namespace nbodygo {
+
+// ---------------------------------------------------------------- GpuStepper
+GpuStepper::GpuStepper(int device, int64_t capacity) : cap_(capacity)
+{
+    const int rc = nb_create(device, capacity, 0, &h_);
+    if (rc != NB_OK) {
+        // no CPU fallback by design: the caller must not silently continue on the host
+        throw std::runtime_error(std::string("[ERROR] nb_create: ") + nb_last_error(nullptr));
+    }
+}
+
+GpuStepper::~GpuStepper()
+{
+    if (h_) nb_destroy(h_);
+}
+
+void GpuStepper::grow(size_t n)
+{
+    for (auto *v : {&x, &y, &z, &vx, &vy, &vz, &mass, &radius, &rest, &ff, &fs})
+        if (v->size() < n) v->resize(n);
+    if (beh.size() < n) { beh.resize(n); flags.resize(n); exists.resize(n); xyz.resize(3 * n); }
+}
+
+static uint8_t flagsOf(const Body &b)
+{
+    uint8_t f = 0;
+    if (b.Exists) f |= NB_F_EXISTS;
+    if (b.fragmenting) f |= NB_F_FRAGMENTING;
+    if (b.Pinned) f |= NB_F_PINNED;
+    if (b.IsSun) f |= NB_F_SUN;
+    if (b.WithTelemetry) f |= NB_F_TELEMETRY;
+    return f;
+}
+
+void GpuStepper::upload(BodyCollection &bc)
+{
+    auto &arr = bc.GetArray();
+    const size_t n = arr.size();
+    if ((int64_t)n > cap_) throw std::runtime_error("[ERROR] body count exceeds the device capacity");
+    grow(n);
+    for (size_t i = 0; i < n; ++i) {
+        const Body &b = *arr[i];
+        x[i] = b.X; y[i] = b.Y; z[i] = b.Z; vx[i] = b.Vx; vy[i] = b.Vy; vz[i] = b.Vz;
+        mass[i] = b.Mass; radius[i] = b.Radius; rest[i] = b.r; ff[i] = b.FragFactor; fs[i] = b.FragStep;
+        beh[i] = (uint8_t)b.Behavior; flags[i] = flagsOf(b);
+    }
+    const int rc = nb_upload(h_, (int64_t)n, x.data(), y.data(), z.data(), vx.data(), vy.data(), vz.data(),
+                             mass.data(), radius.data(), rest.data(), ff.data(), fs.data(), beh.data(), flags.data());
+    if (rc != NB_OK) std::fprintf(stderr, "[ERROR] nb_upload: %s\n", nb_last_error(h_));
+    n_ = (int64_t)n;
+    dirty_ = false;
+    hostStale_ = false;
+    stats_.uploads++;
+}
+
+void GpuStepper::SyncToHost(BodyCollection &bc)
+{
+    if (!hostStale_) return;
+    auto &arr = bc.GetArray();
+    const size_t n = std::min(arr.size(), (size_t)n_);
+    if (n == 0) { hostStale_ = false; return; }
+    grow(n);
+    const int rc = nb_download_state(h_, x.data(), y.data(), z.data(), vx.data(), vy.data(), vz.data(), nullptr,
+                                     nullptr, rest.data(), nullptr, flags.data());
+    if (rc != NB_OK) { std::fprintf(stderr, "[ERROR] nb_download_state: %s\n", nb_last_error(h_)); return; }
+    for (size_t i = 0; i < n; ++i) {
+        Body &b = *arr[i];
+        b.X = x[i]; b.Y = y[i]; b.Z = z[i]; b.Vx = vx[i]; b.Vy = vy[i]; b.Vz = vz[i];
+        b.r = rest[i];
+        b.collided = false;
+    }
+    hostStale_ = false;
+    stats_.downloads++;
+}
+
+bool GpuStepper::Step(BodyCollection &bc, double timeScaling, double R, ResultQueue &rq)
+{
+    auto &arr = bc.GetArray();
+    // fragmenting bodies spawn their fragments on the host, as Body.Compute does (body.go:152-155)
+    for (auto &b : arr) {
+        if (b->Exists && b->fragmenting) {
+            b->fragment(bc);
+            if (!b->Exists) dirty_ = true;
+        }
+    }
+    if (dirty_ || (int64_t)arr.size() != n_) upload(bc);
+    const size_t n = arr.size();
+    nb_step_result res{};
+    const int rc = nb_step(h_, timeScaling, R, NB_STEP_DEFAULT, &res);
+    if (rc != NB_OK) {
+        std::fprintf(stderr, "[ERROR] nb_step: %s\n", nb_last_error(h_));
+        return false;
+    }
+    stats_.last = res;
+    stats_.steps++;
+    stats_.ms_device += res.ms_total;
+    hostStale_ = true;
+    // Renderables from the float32 snapshot (13 B/body) — computation-runner.go:317-320
+    grow(n);
+    if (n > 0 && nb_download_render(h_, xyz.data(), exists.data()) != NB_OK) {
+        std::fprintf(stderr, "[ERROR] nb_download_render: %s\n", nb_last_error(h_));
+        return false;
+    }
+    rq.queue.reserve(n);
+    for (size_t i = 0; i < n; ++i) {
+        Body &b = *arr[i];
+        Renderable r;
+        r.Id = b.Id;
+        if (b.Exists && !exists[i]) {
+            std::fprintf(stderr, "[ERROR] NaN values. id=%d (removing from sim)\n", b.Id);  // body.go:135
+            b.Exists = false;
+        }
+        if (b.Exists) {
+            r.Exists = true;
+            r.X = xyz[3 * i]; r.Y = xyz[3 * i + 1]; r.Z = xyz[3 * i + 2];
+            r.Radius = b.Radius; r.IsSun = b.IsSun; r.Intensity = (float)b.intensity; r.Color = b.Color;
+        }
+        rq.Add(r);
+    }
+    // subsume / fragment decisions go through the reference's own handlers (ProcessMods)
+    if (res.n_host_events > 0) {
+        std::vector<nb_event> ev((size_t)res.n_host_events);
+        int64_t m = 0;
+        nb_get_host_events(h_, ev.data(), (int64_t)ev.size(), &m);
+        SyncToHost(bc);
+        for (int64_t k = 0; k < m; ++k) {
+            const nb_event &e = ev[(size_t)k];
+            if (e.a < 0 || e.b < 0 || (size_t)e.a >= n || (size_t)e.b >= n) continue;
+            if (e.kind == NB_EV_SUBSUME) bc.Enqueue(newSubsume(arr[e.a], arr[e.b]));
+            else if (e.kind == NB_EV_FRAGMENT) bc.Enqueue(newFragment(arr[e.a], arr[e.b], e.f1, e.f2));
+        }
+        bc.ProcessMods();
+        dirty_ = true;  // masses / Exists / fragmenting changed on the host
+    }
+    return true;
+}
+
+// After BodyCollection.Cycle: keep the device array in step with the host array without a full
+// re-upload when only deaths (stable compaction) and/or adds (append) happened.
+void GpuStepper::AfterCycle(BodyCollection &bc, bool arrayChanged, int64_t newCount, double R)
+{
+    if (!arrayChanged || dirty_) return;
+    auto &arr = bc.GetArray();
+    int64_t n_dev = n_;
+    if (stats_.last.n_dead > 0) {
+        if (nb_compact(h_, &n_dev, nullptr, 0) != NB_OK) { dirty_ = true; return; }
+        stats_.compacts++;
+    }
+    const int64_t adds = newCount - n_dev;
+    if (adds < 0 || newCount > cap_) { dirty_ = true; return; }
+    if (adds > 0) {
+        grow((size_t)adds);
+        for (int64_t k = 0; k < adds; ++k) {
+            const Body &b = *arr[(size_t)(n_dev + k)];
+            x[k] = b.X; y[k] = b.Y; z[k] = b.Z; vx[k] = b.Vx; vy[k] = b.Vy; vz[k] = b.Vz;
+            mass[k] = b.Mass; radius[k] = b.Radius; ff[k] = b.FragFactor; fs[k] = b.FragStep;
+            beh[k] = (uint8_t)b.Behavior; flags[k] = flagsOf(b);
+        }
+        if (nb_append(h_, adds, R, x.data(), y.data(), z.data(), vx.data(), vy.data(), vz.data(), mass.data(),
+                      radius.data(), ff.data(), fs.data(), beh.data(), flags.data()) != NB_OK) {
+            dirty_ = true;
+            return;
+        }
+        stats_.appends++;
+    }
+    n_ = newCount;
+}
+
+// ---------------------------------------------------------------- ComputationRunner
+ComputationRunner::ComputationRunner(int workerCnt, double timeScaling, bool /*barnesHut*/, ResultQueueHolder *rqh,
+                                     BodyCollection *bc, int device, int64_t capacity)
+    : workerCnt_(workerCnt), bc_(bc), timeScaling_(timeScaling), rqh_(rqh)
+{
+    if (capacity <= 0) capacity = std::max<int64_t>(4096, 2 * (int64_t)bc->Count() + 4096);
+    stepper_ = std::make_unique<GpuStepper>(device, capacity);
+    bc_->syncFromDevice = [this] { stepper_->SyncToHost(*bc_); };
+}
+
+ComputationRunner::~ComputationRunner()
+{
+    Stop();
+    bc_->syncFromDevice = nullptr;
+}
+
+ComputationRunner &ComputationRunner::SetMaxIterations(int maxIteration)
+{
+    maxIteration_ = maxIteration;
+    return *this;
+}
+
+ComputationRunner &ComputationRunner::Start()
+{
+    stop_ = false;
+    running_ = true;
+    th_ = std::thread([this] { run(); });
+    return *this;
+}
+
+void ComputationRunner::Stop()
+{
+    stop_ = true;
+    if (th_.joinable()) th_.join();
+}
+
+void ComputationRunner::SetWorkers(int workerCnt) { workerCnt_ = workerCnt; }  // no pool to resize
+
+void ComputationRunner::SetTimeScaling(double ts)
+{
+    std::lock_guard<std::mutex> g(ctl_);
+    pendingTs_ = ts;
+    haveTs_ = true;
+}
+
+void ComputationRunner::SetCoefficientOfRestitution(double R)
+{
+    std::lock_guard<std::mutex> g(ctl_);
+    pendingR_ = R;
+    haveR_ = true;
+}
+
+void ComputationRunner::RemoveBodies(int deletes)
+{
+    std::lock_guard<std::mutex> g(ctl_);
+    pendingDel_ = deletes;
+    haveDel_ = true;
+}
+
+// computation-runner.go:176-216
+void ComputationRunner::processDeletes()
+{
+    int delCnt;
+    {
+        std::lock_guard<std::mutex> g(ctl_);
+        if (!haveDel_) return;
+        delCnt = pendingDel_;
+        haveDel_ = false;
+    }
+    stepper_->SyncToHost(*bc_);
+    int removedCnt = 0;
+    if (delCnt == -1) {
+        bc_->IterateOnce([&](Body &b) {
+            if (b.Exists) { b.SetNotExists(); removedCnt++; }
+        });
+    } else if (delCnt > 0) {
+        const int count = bc_->Count();
+        const int step = delCnt > count ? 1 : count / delCnt;
+        int iter = 0;
+        bool shouldRemove = false;
+        bc_->IterateOnce([&](Body &b) {
+            if (iter % step == 0) shouldRemove = true;
+            iter++;
+            // the reference keeps iterating after removedCnt reaches delCnt (`return` only leaves the
+            // closure), so more than delCnt bodies can be removed; restated as is (:198-208)
+            if (shouldRemove && !b.Pinned && b.Exists) {
+                b.SetNotExists();
+                shouldRemove = false;
+                removedCnt++;
+            }
+        });
+    }
+    if (removedCnt) stepper_->MarkDirty();
+    std::fprintf(stderr, "[INFO] Computation runner set %d bodies to not exist\n", removedCnt);
+}
+
+void ComputationRunner::runOneComputation()
+{
+    iterations_++;
+    {
+        std::lock_guard<std::mutex> g(ctl_);
+        if (haveTs_) { timeScaling_ = pendingTs_; haveTs_ = false; }
+        if (haveR_) { R_ = pendingR_; haveR_ = false; }
+    }
+    processDeletes();
+    bc_->HandleGetBody();
+    if (bc_->HandleModBody()) stepper_->MarkDirty();
+    auto [rq, ok] = rqh_->NewResultQueue();
+    if (!ok) {
+        skipped_++;
+        std::this_thread::sleep_for(std::chrono::milliseconds(5));  // :276-279
+        return;
+    }
+    if (bc_->Count() == 0 && bc_->pendingAdds() == 0) {
+        std::this_thread::sleep_for(std::chrono::milliseconds(5));  // no bodies (:313)
+    }
+    stepper_->Step(*bc_, timeScaling_, R_, *rq);
+    rqh_->Add(rq);
+    const bool changed = bc_->Cycle(R_);
+    stepper_->AfterCycle(*bc_, changed, bc_->Count(), R_);
+    computations_++;
+}
+
+void ComputationRunner::run()
+{
+    startTime_ = std::chrono::steady_clock::now();
+    while (!stop_) {
+        runOneComputation();
+        if (maxIteration_ > 0 && --maxIteration_ == 0) break;
+        std::this_thread::yield();
+    }
+    stepper_->SyncToHost(*bc_);
+    stopTime_ = std::chrono::steady_clock::now();
+    running_ = false;
+}
+
+void ComputationRunner::PrintStats()
+{
+    const double totalMillis = std::chrono::duration<double, std::milli>(stopTime_ - startTime_).count();
+    const double fps = totalMillis > 0 ? (double)computations_ / totalMillis * 1000 : 0;
+    const StepStats &s = stepper_->stats();
+    std::printf("Runner\n workerCnt: %d (GPU path: no worker pool)\n iterations: %llu\n computations: %llu\n"
+                " skipped (no queue capacity): %llu\n device ms/computation: %g\n frames per second: %g\n"
+                " elapsed time: %gs\nGpuStepper\n uploads: %llu appends: %llu compacts: %llu downloads: %llu\n",
+                workerCnt_, (unsigned long long)iterations_, (unsigned long long)computations_,
+                (unsigned long long)skipped_, s.steps ? s.ms_device / (double)s.steps : 0.0, fps, totalMillis / 1000,
+                (unsigned long long)s.uploads, (unsigned long long)s.appends, (unsigned long long)s.compacts,
+                (unsigned long long)s.downloads);
+}
+
+}  // namespace nbodygo

@@ -42,6 +42,36 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return SO
 
 
+HOST_DIR = os.path.join(CSRC, "host")
+BIN_DIR = os.path.join(PKG, "bin")
+HOST_LIB_SOURCES = ("host_core.cc", "host_runner.cc", "host_sim.cc")
+HOST_BINARIES = {"host_tests": "host_tests.cc", "nbody_server": "nbody_server.cc"}
+
+
+def build_host(force: bool = False) -> dict:
+    """g++ build of the C++ host mirror (cmd/body, cmd/runner, cmd/sim restated) and its two
+    executables, linked against libnbody_b200.so (rpath $ORIGIN/..)."""
+    build()
+    os.makedirs(BIN_DIR, exist_ok=True)
+    out = {}
+    deps = [os.path.join(HOST_DIR, f) for f in os.listdir(HOST_DIR)] + [SO]
+    newest = max(os.path.getmtime(d) for d in deps)
+    cxx = os.environ.get("CXX", "g++")
+    for name, main_src in HOST_BINARIES.items():
+        exe = os.path.join(BIN_DIR, name)
+        out[name] = exe
+        if not force and os.path.exists(exe) and os.path.getmtime(exe) >= newest:
+            continue
+        cmd = [cxx, "-std=c++17", "-O2", "-Wall", "-Wextra", "-o", exe,
+               *[os.path.join(HOST_DIR, s) for s in HOST_LIB_SOURCES], os.path.join(HOST_DIR, main_src),
+               "-L" + PKG, "-lnbody_b200", "-Wl,-rpath,$ORIGIN/..", "-lpthread"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("g++ failed:\n" + r.stdout + r.stderr)
+    return out
+
+
 if __name__ == "__main__":
     import sys
     print(build(force=True, verbose="-v" in sys.argv))
+    print(build_host(force=True))

@@ -1,0 +1,438 @@
+// host_tests.cc — the reference's own unit tests restated against the C++ host mirror.
+//   host_tests cpu   → tests that need no device (run by pytest -m "not gpu")
+//   host_tests gpu   → tests that step the device through the C ABI (pytest -m gpu)
+// Each test cites the Go test it restates.
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <thread>
+
+#include "nbody_host.h"
+
+using namespace nbodygo;
+
+static int g_fail = 0;
+#define CHECK(cond)                                                              \
+    do {                                                                         \
+        if (!(cond)) {                                                           \
+            std::printf("  FAIL %s:%d: %s\n", __FILE__, __LINE__, #cond);        \
+            g_fail++;                                                            \
+            return;                                                              \
+        }                                                                        \
+    } while (0)
+
+// createTestBody / createTestBodies, cmd/body/body_collection_test.go:15-56
+static BodyPtr createTestBody(int id)
+{
+    auto b = std::make_shared<Body>();
+    b->Id = id;
+    b->Name = std::to_string(id);
+    b->Class = std::to_string(id);
+    b->X = b->Y = b->Z = b->Vx = b->Vy = b->Vz = b->Radius = b->Mass = b->FragFactor = b->FragStep = (double)id;
+    b->Behavior = Elastic;
+    b->Color = Red;
+    b->Exists = true;
+    b->r = 1;
+    return b;
+}
+static std::vector<BodyPtr> createTestBodies(int cnt)
+{
+    std::vector<BodyPtr> v((size_t)cnt);
+    for (int i = 0; i < cnt; ++i) v[(size_t)i] = createTestBody(i);
+    return v;
+}
+
+// ---------------------------------------------------------------- cmd/body/body_test.go
+static void TestMod()
+{
+    auto b = createTestBody(1);
+    b->ApplyMods({"x=41", "y=42", "z=43", "vx=44", "vy=45", "vz=46", "mass=47", "radius=48", "frag-factor=49",
+                  "frag-step=50", "collision=subsume", "color=green", "telemetry=true", "exists=false",
+                  "bogus", "a=b=c", "x=notanumber"});
+    CHECK(b->X == 41 && b->Y == 42 && b->Z == 43 && b->Vx == 44 && b->Vy == 45 && b->Vz == 46);
+    CHECK(b->Mass == 47 && b->Radius == 48 && b->FragFactor == 49 && b->FragStep == 50);
+    CHECK(b->Behavior == Subsume && b->Color == Green && b->WithTelemetry && !b->Exists);
+}
+
+static void TestIdGen()
+{
+    ResetIdGenerator();
+    const int idCnt = 1000, funcCnt = 10;
+    std::vector<std::thread> th;
+    for (int i = 0; i < funcCnt; ++i)
+        th.emplace_back([&] { for (int k = 0; k < idCnt; ++k) NextId(); });
+    for (auto &t : th) t.join();
+    CHECK(NextId() == funcCnt * idCnt);
+}
+
+static void TestGlobalsParsers()
+{
+    CHECK(ParseCollisionBehavior("SUBSUME") == Subsume && ParseCollisionBehavior("nonsense") == Elastic);
+    CHECK(ParseBoolean("Yes") && ParseBoolean("1") && !ParseBoolean("no"));
+    CHECK(ParseBodyColor("PINK") == Pink && ParseBodyColor("mauve") == Random);
+    CHECK(SafeParseFloat("foo", 1.0) == 1.0 && SafeParseFloat("2.5", 1.0) == 2.5);
+}
+
+// ---------------------------------------------------------------- cmd/body/body_collection_test.go
+static void TestInitSize()
+{
+    const int cnt = 1000000;
+    BodyCollection bc(createTestBodies(cnt));
+    CHECK(bc.Count() == cnt);
+}
+
+static void TestRemove()
+{
+    const int cnt = 1000, idToDelete = 10;
+    BodyCollection bc(createTestBodies(cnt));
+    bc.GetArray()[idToDelete]->Exists = false;
+    bc.Cycle(1);
+    CHECK(bc.Count() == cnt - 1);
+    for (auto &b : bc.GetArray()) CHECK(b->Id != idToDelete);
+    for (size_t i = 1; i < bc.GetArray().size(); ++i) CHECK(bc.GetArray()[i - 1]->Id < bc.GetArray()[i]->Id);  // stable
+}
+
+static void TestAdds()
+{
+    const int cnt = 500, idToAdd = 600;
+    BodyCollection bc(createTestBodies(cnt));
+    bc.Enqueue(NewAdd(createTestBody(idToAdd)));
+    bc.Cycle(0.25);
+    CHECK(bc.Count() == cnt + 1);
+    CHECK(bc.GetArray().back()->Id == idToAdd);
+    CHECK(bc.GetArray().back()->r == 0.25);  // arr[j].r = R (body_collection.go:276,288)
+}
+
+static void getBodyCase(int cnt, int id, const std::string &name, int expectId)
+{
+    BodyCollection bc(createTestBodies(cnt));
+    BodyPtr got;
+    bool done = false;
+    std::thread t([&] { got = bc.GetBody(id, name); done = true; });  // blocks until HandleGetBody
+    for (int spin = 0; spin < 2000 && !done; ++spin) {
+        bc.HandleGetBody();
+        std::this_thread::sleep_for(std::chrono::microseconds(100));
+    }
+    t.join();
+    if (expectId < 0) { CHECK(got == nullptr); return; }
+    CHECK(got != nullptr && got->Id == expectId);
+    CHECK(got.get() != bc.GetArray()[(size_t)expectId].get());  // a clone, never the live body
+}
+static void TestGetByID() { getBodyCase(1000, 10, "", 10); }
+static void TestGetByName() { getBodyCase(2000, -1, "1999", 1999); }
+static void TestGetNoMatch() { getBodyCase(100, 5000, "", -1); }
+
+static void modBodyCase(int id, const std::string &name, const std::string &cls, ModBodyResult expect, int checkIdx)
+{
+    BodyCollection bc(createTestBodies(1000));
+    ModBodyResult res = ModBodyResult::ModNone;
+    bool done = false;
+    std::thread t([&] { res = bc.ModBody(id, name, cls, {"color=blue"}); done = true; });
+    for (int spin = 0; spin < 2000 && !done; ++spin) {
+        bc.HandleModBody();
+        std::this_thread::sleep_for(std::chrono::microseconds(100));
+    }
+    t.join();
+    CHECK(res == expect);
+    if (checkIdx >= 0) CHECK(bc.GetArray()[(size_t)checkIdx]->Color == Blue);
+}
+static void TestModByID() { modBodyCase(10, "", "", ModBodyResult::ModAll, 10); }
+static void TestModByIDNoMatch() { modBodyCase(2000, "", "", ModBodyResult::NoMatch, -1); }
+static void TestModByName() { modBodyCase(-1, "10", "", ModBodyResult::ModAll, 10); }
+static void TestModByClass() { modBodyCase(-1, "", "10", ModBodyResult::ModAll, 10); }
+
+static void TestSubsume()
+{
+    const int cnt = 500, idSubsumes = 10, idSubsumed = 444;
+    BodyCollection bc(createTestBodies(cnt));
+    auto &arr = bc.GetArray();
+    bc.Enqueue(newSubsume(arr[idSubsumes], arr[idSubsumed]));
+    bc.ProcessMods();
+    CHECK(arr[idSubsumes]->Exists && !arr[idSubsumed]->Exists);
+    CHECK(arr[idSubsumes]->Mass == 10 + 444 && arr[idSubsumed]->Mass == 0);
+}
+
+static void TestFragmentHostPath()
+{
+    // fragcalc.go: a Fragment body whose factor exceeds FragFactor starts fragmenting and then
+    // spawns at most maxFragsPerCycle+1 elastic fragments per cycle until it is used up
+    BodyCollection bc(createTestBodies(3));
+    auto &arr = bc.GetArray();
+    arr[1]->Behavior = Fragment; arr[1]->FragFactor = 0.25; arr[1]->FragStep = 1000; arr[1]->Mass = 500; arr[1]->Radius = 10;
+    bc.Enqueue(newFragment(arr[1], arr[2], 0.5, 0.0));
+    bc.ProcessMods();
+    CHECK(arr[1]->fragmenting && arr[1]->fragInfo.fragments == 250);
+    arr[1]->fragment(bc);
+    CHECK(bc.pendingAdds() == 101 && arr[1]->Exists);
+    bc.Cycle(1);
+    CHECK(bc.Count() == 3 + 101);
+    arr = bc.GetArray();
+    arr[1]->fragment(bc);
+    arr[1]->fragment(bc);
+    CHECK(!arr[1]->Exists);
+    bc.Cycle(1);
+    CHECK(bc.Count() == 2 + 250);
+    CHECK(bc.GetArray().back()->Behavior == Elastic && bc.GetArray().back()->Mass == 2.0);
+}
+
+// ---------------------------------------------------------------- cmd/runner/resultqueue_test.go
+static void TestResultQueueHolder()
+{
+    ResultQueueHolder rqh(3);
+    std::vector<unsigned> order;
+    for (int k = 0; k < 3; ++k) {
+        auto [q, ok] = rqh.NewResultQueue();
+        CHECK(ok);
+        rqh.Add(q);
+    }
+    CHECK(!rqh.NewResultQueue().second);  // full ⇒ the runner skips the cycle
+    CHECK(rqh.Resize(1));                 // shrink below content keeps what is queued
+    CHECK(!rqh.Resize(1));
+    CHECK(rqh.MaxQueues() == 1 && rqh.Len() == 3);
+    for (int k = 0; k < 3; ++k) {
+        auto [q, ok] = rqh.Next();
+        CHECK(ok);
+        order.push_back(q->QueueNum);
+    }
+    CHECK(order[0] < order[1] && order[1] < order[2]);  // FIFO
+    CHECK(!rqh.Next().second);
+    CHECK(rqh.Resize(10) && rqh.NewResultQueue().second);
+}
+
+static void TestResultQueueSoak()
+{
+    // resultqueue_test.go:19-39 (10 s in the reference; 1 s here): FIFO under add/get/resize
+    ResultQueueHolder rqh(10);
+    std::atomic<bool> stop{false};
+    std::atomic<int> bad{0};
+    std::thread consumer([&] {
+        long last = -1;
+        while (!stop) {
+            auto [q, ok] = rqh.Next();
+            if (ok) { if ((long)q->QueueNum <= last) bad++; last = q->QueueNum; }
+        }
+    });
+    std::thread resizer([&] {
+        int k = 0;
+        while (!stop) { rqh.Resize(5 + (k++ % 10)); std::this_thread::sleep_for(std::chrono::milliseconds(1)); }
+    });
+    const auto t0 = std::chrono::steady_clock::now();
+    while (std::chrono::steady_clock::now() - t0 < std::chrono::seconds(1)) {
+        auto [q, ok] = rqh.NewResultQueue();
+        if (ok) rqh.Add(q);
+    }
+    stop = true;
+    consumer.join();
+    resizer.join();
+    CHECK(bad == 0);
+}
+
+// ---------------------------------------------------------------- cmd/sim (CSV channel, generators)
+static void TestCsvRoundTrip()
+{
+    ResetIdGenerator();
+    auto bodies = Generate("Sim3", 201, Elastic, Random, "", 42);
+    CHECK(bodies.size() == 201 && bodies[0]->IsSun && bodies[0]->Pinned && bodies[0]->Behavior == Subsume);
+    CHECK(WriteCsv("/tmp/nb_host_test.csv", bodies));
+    auto back = FromCsv("/tmp/nb_host_test.csv", 1000, Elastic, Random);
+    CHECK(back.size() == bodies.size());
+    for (size_t i = 0; i < bodies.size(); ++i) {
+        CHECK(back[i]->X == bodies[i]->X && back[i]->Vz == bodies[i]->Vz && back[i]->Mass == bodies[i]->Mass);
+        CHECK(back[i]->Behavior == bodies[i]->Behavior && back[i]->IsSun == bodies[i]->IsSun);
+    }
+    CHECK(FromCsv("/tmp/nb_host_test.csv", 7, Elastic, Random).size() == 7);  // bodyCount caps the read
+    FILE *f = std::fopen("/tmp/nb_host_test2.csv", "w");
+    std::fputs("# comment\n100,100,100,100,100,100,10,.5,,,blue\n1,1,1,1,1,1,10000,10,true,elastic\nbad,row\n"
+               "1,2,3,4,5,6,7,8\n", f);
+    std::fclose(f);
+    auto odd = FromCsv("/tmp/nb_host_test2.csv", 100, Subsume, Red);
+    // row 1 has an empty is_sun field → ParseBool error → skipped, exactly like the reference
+    CHECK(odd.size() == 2 && odd[0]->IsSun && odd[0]->Behavior == Elastic && odd[1]->Behavior == Subsume);
+    CHECK(Generate("NoSuchSim", 10, Elastic, Random, "", 1).empty());
+    CHECK(Generate("SimTest", 0, Elastic, Random, "", 1).size() == 4);
+    CHECK(Generate("Sim5", 0, Elastic, Random, "", 1).back()->Behavior == Fragment);
+}
+
+static void TestNoDeviceFailsLoudly()
+{
+    // without a device the runner must refuse to start: there is no CPU fallback
+    ResultQueueHolder rqh(1);
+    BodyCollection bc({});
+    bool threw = false;
+    try {
+        ComputationRunner cr(1, 1, true, &rqh, &bc);
+    } catch (const std::exception &e) {
+        threw = std::strstr(e.what(), "nb_create") != nullptr;
+    }
+    CHECK(threw);
+}
+
+// ---------------------------------------------------------------- GPU tests
+// cmd/runner/workpool_test.go:41-56 TestWpCompute: two bodies, Vx must become non-zero
+static void TestWpCompute()
+{
+    std::vector<BodyPtr> bodies = {
+        NewBody(1, 1, 1, 1, 0, 0, 0, 1, 1, Elastic, Blue, 0, 0, false, "", "", false),
+        NewBody(2, 22, 22, 22, 0, 0, 0, 1, 1, Elastic, Blue, 0, 0, false, "", "", false)};
+    BodyCollection bc(bodies);
+    ResultQueueHolder rqh(4);
+    ComputationRunner cr(1, 1, false, &rqh, &bc);
+    cr.runOneComputation();
+    cr.Stepper().SyncToHost(bc);
+    CHECK(bc.GetArray()[0]->Vx != 0 && bc.GetArray()[1]->Vx != 0);
+    CHECK(std::fabs(bc.GetArray()[0]->Vx - 2.912062242103079e-14) < 1e-28);  // KAT-1
+    auto [q, ok] = rqh.Next();
+    CHECK(ok && q->Queue().size() == 2 && q->Queue()[0].Exists && q->Queue()[0].Id == 1);
+    CHECK(q->Queue()[1].X == 22.0f);
+}
+
+// cmd/runner/computation-runner_test.go:10-32 TestRunnerSetters
+static void TestRunnerSetters()
+{
+    ResultQueueHolder rqh(1);
+    BodyCollection bc({});
+    ComputationRunner cr(1, 1, true, &rqh, &bc);
+    std::atomic<bool> stop{false};
+    std::thread drain([&] { while (!stop) { rqh.Next(); std::this_thread::yield(); } });
+    cr.Start();
+    cr.SetCoefficientOfRestitution(5);
+    cr.SetTimeScaling(5);
+    cr.SetWorkers(5);
+    std::this_thread::sleep_for(std::chrono::milliseconds(50));
+    CHECK(cr.CoefficientOfRestitution() == 5 && cr.TimeScaling() == 5 && cr.WorkerCount() == 5);
+    cr.Stop();
+    stop = true;
+    drain.join();
+}
+
+// cmd/body/body_collection_test.go:319-344 TestCollide: two bodies at the same point collide; on the
+// device path the NaN velocities are culled in the same cycle (KAT-6) and Cycle removes both
+static void TestCollide()
+{
+    auto bodies = createTestBodies(5000);
+    for (auto &b : bodies) { b->Mass = 1e3; b->Radius = 1; }  // keep every other pair apart (x=y=z=id)
+    bodies[2999]->X = bodies[2999]->Y = bodies[2999]->Z = 500;
+    bodies[3999]->X = bodies[3999]->Y = bodies[3999]->Z = 500;
+    BodyCollection bc(bodies);
+    ResultQueueHolder rqh(4);
+    ComputationRunner cr(1, 1e-9, false, &rqh, &bc);
+    cr.runOneComputation();
+    CHECK(cr.Stepper().stats().last.n_pairs == 2 && cr.Stepper().stats().last.n_resolved >= 1);
+    CHECK(!bodies[2999]->Exists && !bodies[3999]->Exists);
+    CHECK(bc.Count() == 4998);
+    auto [q, ok] = rqh.Next();
+    CHECK(ok && !q->Queue()[2999].Exists && q->Queue()[2998].Exists);
+    cr.runOneComputation();  // the compacted device array keeps working
+    CHECK(cr.Stepper().stats().compacts == 1 && cr.Stepper().stats().uploads == 1);
+    CHECK(cr.Stepper().stats().last.n_bodies == 4998);
+}
+
+// adds / mods / deletes through the runner's control window (computation-runner.go:268-273)
+static void TestControlWindow()
+{
+    ResetIdGenerator();
+    auto bodies = Generate("Sim3", 401, Elastic, Random, "", 7);
+    BodyCollection bc(bodies);
+    ResultQueueHolder rqh(100);
+    ComputationRunner cr(1, 1e-9, false, &rqh, &bc);
+    cr.runOneComputation();
+    // add-body (cmd/sim/grpcsimcb.go:49-62): appended at the end by the next Cycle with r = R
+    cr.SetCoefficientOfRestitution(0.5);
+    bc.Enqueue(NewAdd(NewBody(NextId(), 900, 900, 900, 0, 0, 0, 1e20, 3, Elastic, Blue, 0, 0, false, "added", "", false)));
+    cr.runOneComputation();
+    CHECK(bc.Count() == 402 && bc.GetArray().back()->Name == "added" && bc.GetArray().back()->r == 0.5);
+    CHECK(cr.Stepper().stats().appends == 1);
+    cr.runOneComputation();
+    CHECK(cr.Stepper().stats().last.n_bodies == 402);
+    // mod-body from another thread while the runner cycles
+    ModBodyResult res = ModBodyResult::NoMatch;
+    std::atomic<bool> done{false};
+    std::thread t([&] { res = bc.ModBody(-1, "added", "", {"vx=123", "collision=none"}); done = true; });
+    for (int k = 0; k < 2000 && !done; ++k) cr.runOneComputation();
+    t.join();
+    CHECK(res == ModBodyResult::ModAll);
+    BodyPtr got;
+    done = false;
+    std::thread t2([&] { got = bc.GetBody(-1, "added"); done = true; });
+    for (int k = 0; k < 2000 && !done; ++k) cr.runOneComputation();
+    t2.join();
+    CHECK(got && got->Behavior == None && std::fabs(got->Vx - 123) < 1.0);  // gravity nudged it slightly
+    // remove-bodies: every (count/deletes)-th non-pinned body (computation-runner.go:176-216)
+    const int before = bc.Count();
+    cr.RemoveBodies(10);
+    cr.runOneComputation();
+    CHECK(bc.Count() <= before - 10 && bc.Count() >= before - 12);
+    CHECK(bc.GetArray()[0]->Pinned && bc.GetArray()[0]->Exists);  // the sun is pinned
+    cr.RemoveBodies(-1);
+    cr.runOneComputation();
+    CHECK(bc.Count() == 0);
+    cr.runOneComputation();  // an empty collection still cycles
+    while (rqh.Next().second) {}
+}
+
+// Sim5 end to end: the fragmenting impactor produces fragment decisions on the device, the host
+// spawns the fragments over the following cycles, subsume events shrink the population
+static void TestSubsumeAndFragmentLoop()
+{
+    ResetIdGenerator();
+    std::vector<BodyPtr> bodies = {
+        NewBody(NextId(), 0, 0, 0, 0, 0, 0, 9e20, 100, Subsume, Red, 0, 0, false, "big", "", false),
+        NewBody(NextId(), 50, 0, 0, 0, 0, 0, 1e10, 5, Elastic, Blue, 0, 0, false, "eaten", "", false),
+        NewBody(NextId(), 1000, 0, 0, 1e9, 0, 0, 1e12, 10, Elastic, Green, 0, 0, false, "target", "", false),
+        NewBody(NextId(), 1015, 0, 0, -1e9, 2e8, 0, 1e12, 10, Fragment, Yellow, 0.01, 100, false, "impactor", "", false)};
+    BodyCollection bc(bodies);
+    ResultQueueHolder rqh(100);
+    ComputationRunner cr(1, 1e-12, false, &rqh, &bc);
+    cr.runOneComputation();
+    CHECK(!bodies[1]->Exists && bodies[0]->Mass == 9e20 + 1e10);       // ResolveSubsume on the host
+    CHECK(bodies[3]->fragmenting);                                       // shouldFragment on the device
+    CHECK(bc.Count() == 3);
+    for (int k = 0; k < 4; ++k) cr.runOneComputation();
+    CHECK(!bodies[3]->Exists && bc.Count() > 3);
+    while (rqh.Next().second) {}
+}
+
+static void TestHeadlessRun()
+{
+    ResetIdGenerator();
+    auto bodies = Generate("Sim1", 2000, Elastic, Random, "", 3);
+    const HeadlessResult r = RunHeadless(bodies, 1e-9, -1, 50, 0, true);
+    CHECK(r.computations == 50 && r.finalBodies > 1900 && r.fps > 0);
+    CHECK(std::isfinite(bodies[5]->X) && bodies[5]->X != 0);
+}
+
+int main(int argc, char **argv)
+{
+    const std::string mode = argc > 1 ? argv[1] : "cpu";
+    struct T { const char *name; std::function<void()> fn; };
+    std::vector<T> cpu = {{"TestMod", TestMod}, {"TestIdGen", TestIdGen}, {"TestGlobalsParsers", TestGlobalsParsers},
+                          {"TestInitSize", TestInitSize}, {"TestRemove", TestRemove}, {"TestAdds", TestAdds},
+                          {"TestGetByID", TestGetByID}, {"TestGetByName", TestGetByName},
+                          {"TestGetNoMatch", TestGetNoMatch}, {"TestModByID", TestModByID},
+                          {"TestModByIDNoMatch", TestModByIDNoMatch}, {"TestModByName", TestModByName},
+                          {"TestModByClass", TestModByClass}, {"TestSubsume", TestSubsume},
+                          {"TestFragmentHostPath", TestFragmentHostPath},
+                          {"TestResultQueueHolder", TestResultQueueHolder}, {"TestResultQueueSoak", TestResultQueueSoak},
+                          {"TestCsvRoundTrip", TestCsvRoundTrip}};
+    std::vector<T> nodev = {{"TestNoDeviceFailsLoudly", TestNoDeviceFailsLoudly}};
+    std::vector<T> gpu = {{"TestWpCompute", TestWpCompute}, {"TestRunnerSetters", TestRunnerSetters},
+                          {"TestCollide", TestCollide}, {"TestControlWindow", TestControlWindow},
+                          {"TestSubsumeAndFragmentLoop", TestSubsumeAndFragmentLoop},
+                          {"TestHeadlessRun", TestHeadlessRun}};
+    std::vector<T> *sets[] = {&cpu, nullptr};
+    if (mode == "gpu") sets[0] = &gpu;
+    if (mode == "nodevice") sets[0] = &nodev;
+    int ran = 0;
+    for (auto &t : *sets[0]) {
+        const int before = g_fail;
+        std::printf("RUN  %s\n", t.name);
+        std::fflush(stdout);
+        t.fn();
+        std::printf("%s %s\n", g_fail == before ? "ok  " : "FAIL", t.name);
+        ran++;
+    }
+    std::printf("%d tests, %d failures\n", ran, g_fail);
+    return g_fail ? 1 : 0;
+}

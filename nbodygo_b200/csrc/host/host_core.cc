@@ -158,7 +158,10 @@ static void vectorEven(std::mt19937_64 &rng, double cx, double cy, double cz, do
 
 void Body::fragment(BodyCollection &bc)
 {
-    std::mt19937_64 rng(0x9E3779B97F4A7C15ull ^ ((uint64_t)Id << 20) ^ (uint64_t)fragInfo.fragments);
+    // deterministic stand-in for the reference's clock seed; the cycle number keeps a body that is
+    // re-initiated every cycle from dropping its fragments on top of the previous cycle's
+    std::mt19937_64 rng(0x9E3779B97F4A7C15ull ^ ((uint64_t)Id << 40) ^ ((uint64_t)bc.cycle() << 16) ^
+                        (uint64_t)fragInfo.fragments);
     int cnt = 0;
     while (fragInfo.fragments > 0) {
         fragInfo.fragments--;

@@ -100,7 +100,8 @@ def cpu_pool_rate(bodies, seconds_target: float, workers: int):
     from oracle.oracle import OracleSim
     o = OracleSim(bodies.copy())
     n = bodies.n
-    probe = max(workers, min(n, 4 * workers))
+    o.time_slice(0, min(n, workers), workers)      # loads the library and spins the pool up once, untimed
+    probe = min(n, max(128, 8 * workers))       # >= 100 rows: below that the reference runs a single slice
     while True:   # grow the probe until it is long enough to extrapolate from
         t0 = time.perf_counter()
         o.time_slice(0, probe, workers)
@@ -152,6 +153,19 @@ def run_reference(args):
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def ncu_traffic(n: int, world: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one k_force launch from the committed
+    `ncu --set full` capture of the same workload (profiles/r1_k_force_traffic.json), else None."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r1_k_force_traffic.json")) as f:
+            for rec in json.load(f):
+                if rec["n_bodies"] == n and rec["n_gpus"] == world:
+                    return rec["dram_bytes_per_launch"]
+    except (OSError, ValueError, KeyError):
+        pass
+    return None
 
 
 # ---------------------------------------------------------------- our arm
@@ -274,7 +288,7 @@ def run_ours(args):
             "steps_per_s": args.steps / t_dev,
             "wall_s_timed_region": t_wall,
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak_burst, "unit": "TFLOP/s",
-                         "frac": achieved / peak_burst, "traffic": None,
+                         "frac": achieved / peak_burst, "traffic": ncu_traffic(n, world),
                          "kernel": "k_force", "peak_source": "measured here: DFMA chain (nb_measure_fp64_peak), burst",
                          "peak_sustained": peak_sust, "frac_of_sustained": achieved / peak_sust,
                          "peak_nominal": NOMINAL_FP64_TFLOPS, "frac_of_nominal": achieved / NOMINAL_FP64_TFLOPS,

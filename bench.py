@@ -100,7 +100,11 @@ def cpu_pool_rate(bodies, seconds_target: float, workers: int):
     from oracle.oracle import OracleSim
     o = OracleSim(bodies.copy())
     n = bodies.n
-    o.time_slice(0, min(n, workers), workers)      # loads the library and spins the pool up once, untimed
+    # untimed: load the library, then ~2 s of threaded work so that the host cores reach their
+    # steady clocks / placement (the first second of a burst runs at a fraction of the steady rate)
+    t_w, rows_w = time.perf_counter(), min(n, max(128, 8 * workers))
+    while time.perf_counter() - t_w < 2.0:
+        o.time_slice(0, rows_w, workers)
     probe = min(n, max(128, 8 * workers))       # >= 100 rows: below that the reference runs a single slice
     while True:   # grow the probe until it is long enough to extrapolate from
         t0 = time.perf_counter()

@@ -373,7 +373,11 @@ static void chunking(long long n, int &n_tiles, int &n_chunks, int &tiles_per_ch
 {
     // a function of n only: the per-body summation order never depends on the grid or the rank count
     n_tiles = (int)((n + TJ - 1) / TJ);
-    int s = std::min(n_tiles, MAX_CHUNKS);
+    // enough chunks that the CTA grid has >= ~40 rounds per SM (tail < ~1 %), within [32, MAX_CHUNKS]
+    long long want = n > 0 ? (CHUNK_TARGET_CTAS * 512 + n - 1) / n : 1;
+    if (const char *e = getenv("NB_CHUNKS")) want = atoll(e);  // development override (tools/kbench.py)
+    int cap = (int)std::max<long long>(MIN_CHUNKS, std::min<long long>(want, MAX_CHUNKS));
+    int s = std::min(n_tiles, cap);
     if (s < 1) s = 1;
     tiles_per_chunk = (n_tiles + s - 1) / s;
     if (tiles_per_chunk < 1) tiles_per_chunk = 1;

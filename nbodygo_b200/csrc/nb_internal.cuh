@@ -20,7 +20,10 @@ namespace nb {
 
 constexpr int TJ = 256;      // bodies per j-tile (one bulk copy of 2 KB per field)
 constexpr int NSTAGE = 2;    // smem stages of the j pipeline
-constexpr int MAX_CHUNKS = 32;  // j-chunks per body (partial-sum slots), function of N only
+// j-chunks per body (= partial-sum slots; a function of n only, see chunking() in nb_api.cu)
+constexpr int MIN_CHUNKS = 32;
+constexpr int MAX_CHUNKS = 128;
+constexpr long long CHUNK_TARGET_CTAS = 148 * 2 * 40;  // (n/512) * chunks >= this when possible
 constexpr int MAX_RANKS = 16;
 
 // cmd/body/body.go:19

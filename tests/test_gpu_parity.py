@@ -419,3 +419,44 @@ def test_c4_full_size_sampled_parity(capi):
     rowset = set(rows.tolist())
     assert [tuple(p) for p in pairs if p[0] in rowset] == sorted(ref_pairs)
     assert res.n_pairs == len(pairs)
+
+
+def test_c2_full_size_collisions_off(capi):
+    # BASELINE config 2 at full size: 10,000-body uniform sphere, behaviour None (no events), 3 steps
+    b = clouds.config("C2")
+    steps = run_both(capi, b, 1e-9, 1.0, opts=0, steps=3)
+    o = oracle_sim(b.copy())
+    fx, fy, fz = steps[0]["forces"]
+    for i0 in (0, 5000, 9900):  # __float128 adjudicator on 300 sampled rows
+        ex, ey, ez, fn = o.compute_exact(i0, i0 + 100)
+        sl = slice(i0, i0 + 100)
+        err = np.max(np.abs(np.stack([fx[sl] - ex[sl], fy[sl] - ey[sl], fz[sl] - ez[sl]])), axis=0)
+        assert np.all(err <= FORCE_TOL * fn[sl])
+    last = steps[-1]
+    assert last["res"].n_pairs == 0 and len(last["hev"]) == 0
+    for f in ("x", "y", "z", "vx", "vy", "vz"):
+        r = getattr(last["ref"], f)
+        assert np.allclose(getattr(last["state"], f), r, rtol=1e-10, atol=1e-12 * np.max(np.abs(r))), f
+
+
+def test_c3_dense_full_size_full_cycle(capi):
+    # BASELINE config 3, collision-dense variant (r x 4): one full cycle of 100,000 bodies against the
+    # threaded oracle: the complete pair list bit-exact, every post-step velocity within tolerance
+    b = clouds.config("C3dense")
+    o = oracle_sim(b.copy())
+    o.compute(workers=os.cpu_count() or 8)
+    ref_pairs = o.collision_pairs()
+    assert len(ref_pairs) > 5000
+    o.process_mods()
+    o.update(1e-9, 1.0)
+    sim = capi.Sim(b.n)
+    sim.upload(b)
+    res = sim.step(1e-9, 1.0)
+    assert np.array_equal(sim.pairs(), ref_pairs)
+    got = sim.download()
+    assert res.n_pairs == len(ref_pairs) and res.resolve_rounds >= 2
+    for f in ("vx", "vy", "vz"):
+        assert np.max(np.abs(getattr(got, f) - getattr(o.b, f))) <= 1e-11 * 1e8, f
+    for f in ("x", "y", "z"):
+        assert np.max(np.abs(getattr(got, f) - getattr(o.b, f))) <= 1e-11 * 2000.0, f
+    sim.close()

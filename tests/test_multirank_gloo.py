@@ -119,6 +119,6 @@ def test_plan_is_a_partition_and_depends_on_n_only():
             assert ranges[0][2:] == capi.plan(n, 0, 1)[2:]
         _, _, nc, tpc = capi.plan(n, 0, 1)
         tiles = -(-n // 256)
-        assert 1 <= nc <= 32 and nc * tpc >= tiles
+        assert 1 <= nc <= 128 and nc * tpc >= tiles
     with pytest.raises(capi.NbError):
         capi.plan(10, 2, 2)

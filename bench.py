@@ -306,8 +306,21 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def relaunch_under_torchrun(args):
+    """`python bench.py --gpus N` without a launcher: re-exec as one rank per GPU."""
+    import socket
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+           "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.abspath(__file__)] + sys.argv[1:]
+    raise SystemExit(subprocess.call(cmd))
+
+
 if __name__ == "__main__":
     a = parse()
+    if a.gpus > 1 and "WORLD_SIZE" not in os.environ and a.impl == "ours":
+        relaunch_under_torchrun(a)
     if a.impl == "reference":
         run_reference(a)
     else:

@@ -280,6 +280,10 @@ static int write_range(nb_handle h, long long first, long long count, bool defau
     if (rc) return rc;
     rc = copy_in_u8(h, h->d.flags, flags, first, count, NB_F_EXISTS, defaults);
     if (rc) return rc;
+    if (defaults) {  // a new body starts with fx = fy = fz = 0 (NewBody, body.go:73-75)
+        for (double *f : {h->d.fx, h->d.fy, h->d.fz})
+            NB_CUDA(h, cudaMemsetAsync(f + first, 0, (size_t)count * sizeof(double), h->st));
+    }
     // host buffers may be reused by the caller as soon as we return
     NB_CUDA(h, cudaStreamSynchronize(h->st));
     return NB_OK;

@@ -31,16 +31,18 @@ __global__ void __launch_bounds__(INT_THREADS) k_integrate(const __grid_constant
         unsigned fl = s.flags[i];
         const double m = s.mass[i];
         const double gm = G_CONST() * m;
+        // Body.Compute returns early for !Exists and for fragmenting bodies (body.go:149-155): their
+        // fx,fy,fz keep the value of the last cycle they computed, and Update still applies it
         const bool computes = (fl & NB_F_EXISTS) && !(fl & NB_F_FRAGMENTING);
-        const double fx = computes ? gm * sx : 0.0;
-        const double fy = computes ? gm * sy : 0.0;
-        const double fz = computes ? gm * sz : 0.0;
+        const double fx = computes ? gm * sx : s.fx[i];
+        const double fy = computes ? gm * sy : s.fy[i];
+        const double fz = computes ? gm * sz : s.fz[i];
         s.fx[i] = fx;
         s.fy[i] = fy;
         s.fz[i] = fz;
         if (apply && (fl & NB_F_EXISTS)) {
             double vx = s.vx[i], vy = s.vy[i], vz = s.vz[i];
-            if (!(fl & NB_F_COLLIDED) && computes) {
+            if (!(fl & NB_F_COLLIDED)) {
                 vx += p.ts * fx / m;  // body.go:120-122
                 vy += p.ts * fy / m;
                 vz += p.ts * fz / m;

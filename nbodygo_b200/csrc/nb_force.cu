@@ -214,6 +214,51 @@ __device__ __noinline__ double exact_pair(const StepParams &p, long long i, long
     return 0.0;
 }
 
+// ---------------------------------------------------------------- K1: fast pass over one tile
+// Two j-bodies per iteration (LDS.128), R i-bodies per thread.  SELF: the tile holds bodies of this
+// CTA; the pair (i,i) gets the seed 0 (hence w == 0 exactly) and is left out of the minimum.
+template <int R, int UNR, bool SELF>
+__device__ __forceinline__ void fast_tile(const double *sx, const double *sy, const double *sz, const double *sj,
+                                          const double (&xi)[R], const double (&yi)[R], const double (&zi)[R],
+                                          const unsigned (&zlo)[2 * R], const int (&self_j)[R], double (&tx)[R],
+                                          double (&ty)[R], double (&tz)[R], unsigned (&lo)[R])
+{
+#pragma unroll(UNR)
+    for (int jj = 0; jj < TJ; jj += 2) {
+        const double2 vx = *reinterpret_cast<const double2 *>(sx + jj);
+        const double2 vy = *reinterpret_cast<const double2 *>(sy + jj);
+        const double2 vz = *reinterpret_cast<const double2 *>(sz + jj);
+        const double2 vm = *reinterpret_cast<const double2 *>(sj + jj);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const double dxa = __dsub_rn(vx.x, xi[r]), dxb = __dsub_rn(vx.y, xi[r]);
+            const double dya = __dsub_rn(vy.x, yi[r]), dyb = __dsub_rn(vy.y, yi[r]);
+            const double dza = __dsub_rn(vz.x, zi[r]), dzb = __dsub_rn(vz.y, zi[r]);
+            const double d2a = __fma_rn(dza, dza, __fma_rn(dya, dya, __dmul_rn(dxa, dxa)));
+            const double d2b = __fma_rn(dzb, dzb, __fma_rn(dyb, dyb, __dmul_rn(dxb, dxb)));
+            unsigned ha = (unsigned)__double2hiint(d2a), hb = (unsigned)__double2hiint(d2b);
+            double ya = rsqrt_seed_lo(d2a, zlo[2 * r]);
+            double yb = rsqrt_seed_lo(d2b, zlo[2 * r + 1]);
+            if (SELF) {
+                const bool sa = jj == self_j[r], sb = jj + 1 == self_j[r];
+                ha = sa ? 0xFFFFFFFFu : ha;
+                hb = sb ? 0xFFFFFFFFu : hb;
+                ya = __hiloint2double(sa ? 0 : __double2hiint(ya), __double2loint(ya));
+                yb = __hiloint2double(sb ? 0 : __double2hiint(yb), __double2loint(yb));
+            }
+            lo[r] = min(lo[r], min(ha, hb));
+            const double wa = w_from_seed(ya, d2a, vm.x);
+            const double wb = w_from_seed(yb, d2b, vm.y);
+            tx[r] = __fma_rn(wa, dxa, tx[r]);
+            ty[r] = __fma_rn(wa, dya, ty[r]);
+            tz[r] = __fma_rn(wa, dza, tz[r]);
+            tx[r] = __fma_rn(wb, dxb, tx[r]);
+            ty[r] = __fma_rn(wb, dyb, ty[r]);
+            tz[r] = __fma_rn(wb, dzb, tz[r]);
+        }
+    }
+}
+
 // ---------------------------------------------------------------- K1: kernel
 // UNR = unroll of the j-group loop (each group is two j-bodies).
 template <int R, int NT, int MINB, int UNR>
@@ -298,30 +343,19 @@ __global__ void __launch_bounds__(NT, MINB) k_force(const __grid_constant__ Step
         const long long jt0 = (long long)(t0 + t) * TJ;
 
         // ---- fast pass: branch-free and unmasked (speculative); only the running minimum of
-        //      hi(d2) is kept per body
-#pragma unroll(UNR)
-        for (int jj = 0; jj < TJ; jj += 2) {
-            const double2 vx = *reinterpret_cast<const double2 *>(sx + jj);
-            const double2 vy = *reinterpret_cast<const double2 *>(sy + jj);
-            const double2 vz = *reinterpret_cast<const double2 *>(sz + jj);
-            const double2 vm = *reinterpret_cast<const double2 *>(sj + jj);
+        //      hi(d2) is kept per body.  A tile that contains bodies of this CTA uses the SELF
+        //      variant, which masks the pair (i,i) (d2 = 0) so that it neither poisons the sums nor
+        //      forces a redo.
+        if (jt0 < ibase + (long long)NT * R && jt0 + TJ > ibase) {
+            int self_j[R];
 #pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const double dxa = __dsub_rn(vx.x, xi[r]), dxb = __dsub_rn(vx.y, xi[r]);
-                const double dya = __dsub_rn(vy.x, yi[r]), dyb = __dsub_rn(vy.y, yi[r]);
-                const double dza = __dsub_rn(vz.x, zi[r]), dzb = __dsub_rn(vz.y, zi[r]);
-                const double d2a = __fma_rn(dza, dza, __fma_rn(dya, dya, __dmul_rn(dxa, dxa)));
-                const double d2b = __fma_rn(dzb, dzb, __fma_rn(dyb, dyb, __dmul_rn(dxb, dxb)));
-                lo[r] = min(lo[r], min((unsigned)__double2hiint(d2a), (unsigned)__double2hiint(d2b)));
-                const double wa = w_from_seed(rsqrt_seed_lo(d2a, zlo[2 * r]), d2a, vm.x);
-                const double wb = w_from_seed(rsqrt_seed_lo(d2b, zlo[2 * r + 1]), d2b, vm.y);
-                tx[r] = __fma_rn(wa, dxa, tx[r]);
-                ty[r] = __fma_rn(wa, dya, ty[r]);
-                tz[r] = __fma_rn(wa, dza, tz[r]);
-                tx[r] = __fma_rn(wb, dxb, tx[r]);
-                ty[r] = __fma_rn(wb, dyb, ty[r]);
-                tz[r] = __fma_rn(wb, dzb, tz[r]);
-            }
+            for (int r = 0; r < R; ++r) self_j[r] = (int)(ibase + (long long)r * NT + tid - jt0);
+            fast_tile<R, UNR, true>(sx, sy, sz, sj, xi, yi, zi, zlo, self_j, tx, ty, tz, lo);
+        } else {
+            int self_j[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) self_j[r] = -1;
+            fast_tile<R, UNR, false>(sx, sy, sz, sj, xi, yi, zi, zlo, self_j, tx, ty, tz, lo);
         }
 
         // ---- commit, or (rare) redo the tile carefully for a body that saw a screened pair.

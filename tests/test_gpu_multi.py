@@ -80,3 +80,66 @@ def test_sharded_step_equals_single_gpu(world, n):
             assert np.array_equal(o["flags"], st.flags) and np.array_equal(o["rest"], st.rest)
             assert o["n_pairs"] == res.n_pairs and o["n_dead"] == res.n_dead and o["resolved"] == res.n_resolved
     sim.close()
+
+
+def _rank_sync_ops(rank, world, n, q_uid, q_out):
+    """Cycle-top state sync on every rank: deletes (SetNotExists) + compaction + appends between steps."""
+    from nbodygo_b200 import capi
+    from nbodygo_b200.bodies import BodyArrays
+    b = clouds.uniform_cube(n, 90.0, 1.6, 1e12, vmax=50.0, seed=78)
+    sim = capi.Sim(b.n + 64, device=rank)
+    sim.upload(b)
+    if rank == 0:
+        uid = capi.comm_unique_id()
+        for _ in range(world - 1):
+            q_uid.put(uid)
+    else:
+        uid = q_uid.get(timeout=120)
+    sim.comm_init(rank, world, uid)
+    sim.step(1e-3, 1.0)
+    for i in (7, n // 2, n - 1):
+        sim.patch(i, 1, mass=np.zeros(1), flags=np.zeros(1, dtype=np.uint8))
+    new_n, _ = sim.compact()
+    add = clouds.uniform_cube(5, 20.0, 1.0, 1e12, seed=3)
+    sim.append(add, R=0.5)
+    res = sim.step(1e-3, 0.5)
+    st = sim.download()
+    q_out.put((rank, dict(new_n=new_n, n=sim.count(), x=st.x, vx=st.vx, rest=st.rest, pairs=sim.pairs(),
+                          n_pairs=res.n_pairs, shard=sim.shard_range())))
+    sim.close()
+
+
+def test_state_sync_ops_on_two_gpus():
+    world, n = 2, 3001
+    if _ndev() < world:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    from nbodygo_b200 import capi
+    ctx = mp.get_context("spawn")
+    q_uid, q_out = ctx.Queue(), ctx.Queue()
+    procs = [ctx.Process(target=_rank_sync_ops, args=(r, world, n, q_uid, q_out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(q_out.get(timeout=300) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    b = clouds.uniform_cube(n, 90.0, 1.6, 1e12, vmax=50.0, seed=78)
+    sim = capi.Sim(b.n + 64)
+    sim.upload(b)
+    sim.step(1e-3, 1.0)
+    for i in (7, n // 2, n - 1):
+        sim.patch(i, 1, mass=np.zeros(1), flags=np.zeros(1, dtype=np.uint8))
+    new_n, _ = sim.compact()
+    sim.append(clouds.uniform_cube(5, 20.0, 1.0, 1e12, seed=3), R=0.5)
+    res = sim.step(1e-3, 0.5)
+    st = sim.download()
+    for r in range(world):
+        o = got[r]
+        assert o["new_n"] == new_n == n - 3 and o["n"] == n + 2
+        assert np.array_equal(o["x"].view(np.uint64), st.x.view(np.uint64))
+        assert np.array_equal(o["vx"].view(np.uint64), st.vx.view(np.uint64))
+        assert np.array_equal(o["rest"], st.rest) and np.array_equal(o["pairs"], sim.pairs())
+        assert o["n_pairs"] == res.n_pairs
+    assert got[0]["shard"][1] == got[1]["shard"][0]
+    sim.close()

@@ -460,3 +460,53 @@ def test_c3_dense_full_size_full_cycle(capi):
     for f in ("x", "y", "z"):
         assert np.max(np.abs(getattr(got, f) - getattr(o.b, f))) <= 1e-11 * 2000.0, f
     sim.close()
+
+
+def test_async_step_and_sync(capi):
+    # NB_STEP_ASYNC enqueues the cycle; nb_sync collects the same result a synchronous step gives
+    b = clouds.uniform_cube(2000, 150.0, 1.5, 1e13, vmax=20.0, seed=51)
+    s1, s2 = capi.Sim(b.n), capi.Sim(b.n)
+    s1.upload(b)
+    s2.upload(b)
+    r1 = s1.step(1e-3, 1.0)
+    s2.step(1e-3, 1.0, capi.STEP_DEFAULT | capi.STEP_ASYNC)
+    r2 = s2.sync()
+    assert (r1.n_pairs, r1.n_resolved, r1.n_dead) == (r2.n_pairs, r2.n_resolved, r2.n_dead) and r1.n_pairs > 0
+    a, c = s1.download(), s2.download()
+    assert np.array_equal(a.x.view(np.uint64), c.x.view(np.uint64))
+    assert np.array_equal(a.vx.view(np.uint64), c.vx.view(np.uint64))
+    s1.close()
+    s2.close()
+
+
+def test_no_resolve_hands_pairs_to_host(capi):
+    # NB_STEP_NO_RESOLVE: detection only — velocities are those of a collision-free cycle, the pair
+    # list is still complete, collided flags stay clear
+    b = clouds.uniform_cube(1500, 60.0, 2.5, 1e12, vmax=100.0, seed=21)
+    o = oracle_sim(b.copy())
+    o.compute()
+    ref_pairs = o.collision_pairs()
+    o.update(1e-4, 1.0)            # no ProcessMods
+    sim = capi.Sim(b.n)
+    sim.upload(b)
+    res = sim.step(1e-4, 1.0, capi.STEP_COLLISIONS | capi.STEP_NO_RESOLVE)
+    assert res.n_resolved == 0 and res.n_pairs == len(ref_pairs)
+    assert np.array_equal(sim.pairs(), ref_pairs)
+    g = sim.download()
+    for f in ("vx", "x"):
+        r = getattr(o.b, f)
+        assert np.allclose(getattr(g, f), r, rtol=1e-11, atol=1e-12 * np.max(np.abs(r)))
+    sim.close()
+
+
+def test_no_integrate_is_side_effect_free_on_state(capi):
+    b = clouds.uniform_cube(800, 60.0, 2.0, 1e12, vmax=10.0, seed=5)
+    sim = capi.Sim(b.n)
+    sim.upload(b)
+    sim.step(1e-3, 1.0, capi.STEP_COLLISIONS | capi.STEP_NO_INTEGRATE)
+    g = sim.download()
+    for f in ("x", "y", "z", "vx", "vy", "vz", "rest"):
+        assert np.array_equal(getattr(g, f), getattr(b, f)), f
+    assert np.array_equal(g.flags, b.flags)
+    assert len(sim.pairs()) > 0
+    sim.close()

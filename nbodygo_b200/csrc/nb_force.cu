@@ -447,15 +447,9 @@ int launch_force(const StepParams &p, cudaStream_t st, int force_R)
         case 3: return launch_force_t<3, 128, 1, 1>(p, st);
         case 2004: return launch_force_t<4, 128, 1, 2>(p, st);
         case 2002: return launch_force_t<2, 128, 1, 2>(p, st);
-        case 2014: return launch_force_t<4, 256, 1, 2>(p, st);
         case 1012: return launch_force_t<2, 256, 1, 1>(p, st);
         case 1022: return launch_force_t<2, 64, 1, 1>(p, st);
-        case 1024: return launch_force_t<4, 64, 1, 1>(p, st);
-        case 1021: return launch_force_t<1, 64, 1, 2>(p, st);
         case 304: return launch_force_t<4, 128, 3, 1>(p, st);
-        case 303: return launch_force_t<3, 128, 3, 1>(p, st);
-        case 403: return launch_force_t<3, 128, 4, 1>(p, st);
-        case 502: return launch_force_t<2, 128, 5, 1>(p, st);
         default: return launch_force_t<1, 128, 1, 2>(p, st);
     }
 }

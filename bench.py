@@ -40,7 +40,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="C4")
-    ap.add_argument("--n", type=int, default=0, help="override the body count (development only)")
+    ap.add_argument("--bodies", dest="n", type=int, default=0, help="override the body count (development only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--time-scaling", type=float, default=1e-9)

@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <dlfcn.h>
+#include <unistd.h>
 #include <string>
 #include <vector>
 
@@ -91,6 +92,12 @@ struct nb_sim {
     long long launches = 0;
     int force_R = 0;
     StepParams last_params{};
+    // fused peer-memory exchange (K4 pushes the shard state into every peer's replica)
+    bool peer_push = false;
+    PeerTable *d_peers = nullptr;
+    unsigned long long *d_sync = nullptr;  // my flag block: 2*MAX_RANKS slots
+    unsigned long long step_id = 0;
+    std::vector<void *> ipc_opened;
 };
 
 #define NB_CUDA(h, call)                                                                              \
@@ -135,7 +142,10 @@ static void free_all(nb_handle h)
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->st) cudaStreamSynchronize(h->st);
+    for (void *q : h->ipc_opened) cudaIpcCloseMemHandle(q);
     if (h->comm && g_nccl.ok) g_nccl.CommDestroy(h->comm);
+    cudaFree(h->d_peers);
+    cudaFree(h->d_sync);
     for (int k = 0; k < N_F64; ++k) cudaFree(*f64_fields(h->d, k));
     cudaFree(h->d.jx); cudaFree(h->d.jy); cudaFree(h->d.jz);
     cudaFree(h->d.jm); cudaFree(h->d.fx); cudaFree(h->d.fy); cudaFree(h->d.fz);
@@ -344,20 +354,34 @@ extern "C" int nb_compact(nb_handle h, int64_t *n_out, int64_t *old_index, int64
     NB_CUDA(h, cudaSetDevice(h->device));
     const long long n_old = h->n;
     h->launches += launch_compact_map(h->d, n_old, h->d_map, h->d_block_sums, h->d_new_n, h->st);
-    for (int k = 0; k < N_F64; ++k) {
-        double **f = f64_fields(h->d, k);
+    // gather through the scratch buffer; peers hold mapped pointers to these arrays, so with the
+    // peer exchange active the result is copied back instead of swapping the pointers
+    auto settle_f64 = [&](double **f) -> int {
         h->launches += launch_gather_f64(*f, h->scratch_f64, h->d_map, h->d_new_n, n_old, h->st);
-        std::swap(*f, h->scratch_f64);
-    }
+        if (h->peer_push) {
+            NB_CUDA(h, cudaMemcpyAsync(*f, h->scratch_f64, (size_t)n_old * sizeof(double), cudaMemcpyDeviceToDevice,
+                                       h->st));
+        } else {
+            std::swap(*f, h->scratch_f64);
+        }
+        return NB_OK;
+    };
+    auto settle_u8 = [&](uint8_t **f) -> int {
+        h->launches += launch_gather_u8(*f, h->scratch_u8, h->d_map, h->d_new_n, n_old, h->st);
+        if (h->peer_push) {
+            NB_CUDA(h, cudaMemcpyAsync(*f, h->scratch_u8, (size_t)n_old, cudaMemcpyDeviceToDevice, h->st));
+        } else {
+            std::swap(*f, h->scratch_u8);
+        }
+        return NB_OK;
+    };
+    for (int k = 0; k < N_F64; ++k)
+        if (int rc = settle_f64(f64_fields(h->d, k))) return rc;
     double **outs[] = {&h->d.fx, &h->d.fy, &h->d.fz};
-    for (auto f : outs) {
-        h->launches += launch_gather_f64(*f, h->scratch_f64, h->d_map, h->d_new_n, n_old, h->st);
-        std::swap(*f, h->scratch_f64);
-    }
-    h->launches += launch_gather_u8(h->d.behavior, h->scratch_u8, h->d_map, h->d_new_n, n_old, h->st);
-    std::swap(h->d.behavior, h->scratch_u8);
-    h->launches += launch_gather_u8(h->d.flags, h->scratch_u8, h->d_map, h->d_new_n, n_old, h->st);
-    std::swap(h->d.flags, h->scratch_u8);
+    for (auto f : outs)
+        if (int rc = settle_f64(f)) return rc;
+    if (int rc = settle_u8(&h->d.behavior)) return rc;
+    if (int rc = settle_u8(&h->d.flags)) return rc;
     NB_CUDA(h, cudaMemcpyAsync(h->h_new_n, h->d_new_n, sizeof(long long), cudaMemcpyDeviceToHost, h->st));
     NB_CUDA(h, cudaStreamSynchronize(h->st));
     const long long n_new = n_old > 0 ? *h->h_new_n : 0;
@@ -429,6 +453,8 @@ static int finish_step(nb_handle h, nb_step_result *out)
         h->pending = false;
     }
     if (out) *out = h->last;
+    if (h->h_ctr->peer_timeout)
+        return fail(h, NB_ERR_COMM, "peer exchange timed out: a rank did not reach this cycle");
     if (h->last.pair_overflow == 1)
         return fail(h, NB_ERR_PAIR_OVERFLOW, "collision pair capacity exceeded; step not applied");
     return NB_OK;
@@ -483,6 +509,8 @@ extern "C" int nb_step(nb_handle h, double time_scaling, double R, uint32_t opts
     h->d.pair_counts = h->d_pair_counts;
     p.seg_stride = h->seg_cap;
     p.s = h->d;
+    p.peers = (h->peer_push && !(opts & NB_STEP_NO_INTEGRATE)) ? h->d_peers : nullptr;
+    p.step_id = ++h->step_id;
 
     NB_CUDA(h, cudaEventRecord(h->ev[0], h->st));
     NB_CUDA(h, cudaMemsetAsync(h->d.ctr, 0, sizeof(Counters), h->st));
@@ -497,18 +525,31 @@ extern "C" int nb_step(nb_handle h, double time_scaling, double R, uint32_t opts
     NB_CUDA(h, cudaEventRecord(h->ev[3], h->st));
     if (opts & NB_STEP_COLLISIONS) h->launches += launch_resolve(p, h->st);
     NB_CUDA(h, cudaEventRecord(h->ev[4], h->st));
+    const bool advance = !(opts & NB_STEP_NO_INTEGRATE);
+    if (h->peer_push && advance) {
+        // nobody may overwrite my replica before I have finished reading this cycle's inputs (K1, K3),
+        // and I may not overwrite a peer's before it has: publish "done reading", wait for everyone's
+        h->launches += launch_peer_signal(p, MAX_RANKS, h->st);
+        h->launches += launch_peer_wait(p, MAX_RANKS, h->st);
+    }
     h->launches += launch_integrate(p, h->st);
     NB_CUDA(h, cudaEventRecord(h->ev[5], h->st));
     if (h->nranks > 1) {
-        if (!(opts & NB_STEP_NO_INTEGRATE)) {
-            NB_NCCL(h, g_nccl.GroupStart());
-            double *arrs[] = {h->d.x, h->d.y, h->d.z, h->d.vx, h->d.vy, h->d.vz, h->d.rest};
-            for (double *a : arrs)
-                NB_NCCL(h, g_nccl.AllGather(a + (long long)h->rank * shard, a, (size_t)shard, NCCL_FLOAT64, h->comm,
-                                            h->st));
-            NB_NCCL(h, g_nccl.AllGather(h->d.flags + (long long)h->rank * shard, h->d.flags, (size_t)shard,
-                                        NCCL_UINT8, h->comm, h->st));
-            NB_NCCL(h, g_nccl.GroupEnd());
+        if (advance) {
+            if (h->peer_push) {
+                // K4 already stored the shard into every peer; wait until every peer's shard has landed here
+                h->launches += launch_peer_signal(p, 0, h->st);
+                h->launches += launch_peer_wait(p, 0, h->st);
+            } else {
+                NB_NCCL(h, g_nccl.GroupStart());
+                double *arrs[] = {h->d.x, h->d.y, h->d.z, h->d.vx, h->d.vy, h->d.vz, h->d.rest};
+                for (double *a : arrs)
+                    NB_NCCL(h, g_nccl.AllGather(a + (long long)h->rank * shard, a, (size_t)shard, NCCL_FLOAT64,
+                                                h->comm, h->st));
+                NB_NCCL(h, g_nccl.AllGather(h->d.flags + (long long)h->rank * shard, h->d.flags, (size_t)shard,
+                                            NCCL_UINT8, h->comm, h->st));
+                NB_NCCL(h, g_nccl.GroupEnd());
+            }
         }
         h->launches += launch_count_dead(p, h->st);
     }
@@ -639,6 +680,92 @@ extern "C" int nb_comm_unique_id(void *id128)
     return NB_OK;
 }
 
+// Maps every peer's replica of the arrays K4 updates (CUDA IPC across processes, plain UVA pointers
+// + peer access inside one process) so that K4 can store its shard straight into them.  All ranks
+// agree on the outcome: if any rank cannot map a peer, everybody falls back to the NCCL all-gather.
+namespace {
+struct PeerInfo {
+    cudaIpcMemHandle_t ipc[9];
+    unsigned long long raw[9];
+    long long pid;
+    int device, ok;
+};
+}  // namespace
+
+static int setup_peer_push(nb_handle h)
+{
+    const int P = h->nranks;
+    NB_CUDA(h, cudaMalloc((void **)&h->d_sync, 2 * MAX_RANKS * sizeof(unsigned long long)));
+    NB_CUDA(h, cudaMemset(h->d_sync, 0, 2 * MAX_RANKS * sizeof(unsigned long long)));
+    void *mine[9] = {h->d.x, h->d.y, h->d.z, h->d.vx, h->d.vy, h->d.vz, h->d.rest, h->d.flags, h->d_sync};
+    std::vector<PeerInfo> info((size_t)P);
+    PeerInfo &me = info[(size_t)h->rank];
+    memset(&me, 0, sizeof me);
+    me.ok = 1;
+    me.pid = (long long)getpid();
+    me.device = h->device;
+    for (int k = 0; k < 9; ++k) {
+        me.raw[k] = (unsigned long long)(uintptr_t)mine[k];
+        if (cudaIpcGetMemHandle(&me.ipc[k], mine[k]) != cudaSuccess) { me.ok = 0; cudaGetLastError(); }
+    }
+    PeerInfo *d_info = nullptr;
+    NB_CUDA(h, cudaMalloc((void **)&d_info, (size_t)P * sizeof(PeerInfo)));
+    auto gather = [&]() -> int {
+        NB_CUDA(h, cudaMemcpyAsync(d_info + h->rank, &me, sizeof(PeerInfo), cudaMemcpyHostToDevice, h->st));
+        NB_NCCL(h, g_nccl.AllGather(d_info + h->rank, d_info, sizeof(PeerInfo), NCCL_UINT8, h->comm, h->st));
+        NB_CUDA(h, cudaMemcpyAsync(info.data(), d_info, (size_t)P * sizeof(PeerInfo), cudaMemcpyDeviceToHost, h->st));
+        NB_CUDA(h, cudaStreamSynchronize(h->st));
+        return NB_OK;
+    };
+    const PeerInfo mine_copy = me;
+    if (int rc = gather()) { cudaFree(d_info); return rc; }
+    PeerTable t;
+    memset(&t, 0, sizeof t);
+    int ok = 1;
+    for (int q = 0; q < P && ok; ++q) ok = info[(size_t)q].ok;
+    void **slots[9] = {(void **)t.x, (void **)t.y, (void **)t.z, (void **)t.vx, (void **)t.vy, (void **)t.vz,
+                       (void **)t.rest, (void **)t.flags, (void **)t.sync};
+    for (int q = 0; q < P && ok; ++q) {
+        const PeerInfo &pi = info[(size_t)q];
+        for (int k = 0; k < 9 && ok; ++k) {
+            void *ptr = nullptr;
+            if (q == h->rank) {
+                ptr = mine[k];
+            } else if (pi.pid == mine_copy.pid) {
+                // same process (one host driving several handles): UVA pointer + peer access
+                cudaError_t e = cudaDeviceEnablePeerAccess(pi.device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) ok = 0;
+                cudaGetLastError();
+                ptr = (void *)(uintptr_t)pi.raw[k];
+            } else {
+                if (cudaIpcOpenMemHandle(&ptr, pi.ipc[k], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                    ok = 0;
+                    cudaGetLastError();
+                } else {
+                    h->ipc_opened.push_back(ptr);
+                }
+            }
+            slots[k][q] = ptr;
+        }
+    }
+    // second round: everybody must have succeeded, otherwise everybody uses NCCL
+    me = mine_copy;
+    me.ok = ok;
+    if (int rc = gather()) { cudaFree(d_info); return rc; }
+    for (int q = 0; q < P; ++q) ok = ok && info[(size_t)q].ok;
+    cudaFree(d_info);
+    if (!ok) {
+        h->peer_push = false;
+        h->err = "peer-memory exchange unavailable (IPC / peer access failed); using NCCL all-gather";
+        return NB_OK;
+    }
+    NB_CUDA(h, cudaMalloc((void **)&h->d_peers, sizeof(PeerTable)));
+    NB_CUDA(h, cudaMemcpy(h->d_peers, &t, sizeof(PeerTable), cudaMemcpyHostToDevice));
+    h->peer_push = true;
+    h->step_id = 0;
+    return NB_OK;
+}
+
 extern "C" int nb_comm_init(nb_handle h, int rank, int nranks, const void *id128)
 {
     if (!h || !id128 || nranks < 1 || nranks > MAX_RANKS || rank < 0 || rank >= nranks)
@@ -655,6 +782,11 @@ extern "C" int nb_comm_init(nb_handle h, int rank, int nranks, const void *id128
     if (nranks > 1) {
         h->d.pairs_all = nullptr;
         NB_CUDA(h, cudaMalloc((void **)&h->d.pairs_all, (size_t)h->seg_cap * nranks * sizeof(int2)));
+        const char *e = getenv("NB_PEER_PUSH");
+        if (!e || atoi(e) != 0) {
+            int rc = setup_peer_push(h);
+            if (rc != NB_OK) return rc;
+        }
     }
     return NB_OK;
 }

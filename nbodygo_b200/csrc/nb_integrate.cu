@@ -63,6 +63,18 @@ __global__ void __launch_bounds__(INT_THREADS) k_integrate(const __grid_constant
                 culled = 1;
             }
             s.flags[i] = (uint8_t)fl;
+            // fused exchange: the shard's new state goes straight into every peer's replica (NVLink
+            // peer stores, coalesced over i) instead of a separate all-gather
+            if (p.peers) {
+                const PeerTable &pt = *p.peers;
+                for (int q = 0; q < p.nranks; ++q) {
+                    if (q == p.rank) continue;
+                    pt.x[q][i] = x; pt.y[q][i] = y; pt.z[q][i] = z;
+                    pt.vx[q][i] = vx; pt.vy[q][i] = vy; pt.vz[q][i] = vz;
+                    pt.rest[q][i] = p.R;
+                    pt.flags[q][i] = (uint8_t)fl;
+                }
+            }
         }
         // NewRenderable
         const bool ex = (fl & NB_F_EXISTS) != 0;
@@ -95,6 +107,52 @@ __global__ void __launch_bounds__(INT_THREADS) k_count_dead(const __grid_constan
     const int dead = (i < p.n && !(p.s.flags[i] & NB_F_EXISTS)) ? 1 : 0;
     const unsigned dm = __ballot_sync(0xffffffffu, dead);
     if ((threadIdx.x & 31) == 0 && dm) atomicAdd(&p.s.ctr->n_dead, (unsigned long long)__popc(dm));
+}
+
+// ---------------------------------------------------------------- peer flag protocol
+// One thread per peer: publish `step_id` in slot (slot_base + my rank) of every peer's flag block.
+// Stream order guarantees the preceding kernel (K3 / K4) has completed, so its peer stores are done.
+__global__ void k_peer_signal(const __grid_constant__ StepParams p, int slot_base)
+{
+    const int q = threadIdx.x;
+    if (q < p.nranks && q != p.rank) {
+        __threadfence_system();
+        volatile unsigned long long *f = p.peers->sync[q] + slot_base + p.rank;
+        *f = p.step_id;
+        __threadfence_system();
+    }
+}
+
+// One thread per peer: wait until every peer has published >= step_id in my flag block.  Bounded
+// (20 s of globaltimer) so that a lost peer turns into an error flag, never into a hung GPU.
+__global__ void k_peer_wait(const __grid_constant__ StepParams p, int slot_base)
+{
+    const int q = threadIdx.x;
+    if (q < p.nranks && q != p.rank) {
+        volatile unsigned long long *f = p.peers->sync[p.rank] + slot_base + q;
+        unsigned long long t0, t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        while (*f < p.step_id) {
+            __nanosleep(200);
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > 20000000000ull) {
+                p.s.ctr->peer_timeout = 1;
+                break;
+            }
+        }
+        __threadfence_system();
+    }
+}
+
+int launch_peer_signal(const StepParams &p, int slot_base, cudaStream_t st)
+{
+    k_peer_signal<<<1, MAX_RANKS, 0, st>>>(p, slot_base);
+    return 1;
+}
+int launch_peer_wait(const StepParams &p, int slot_base, cudaStream_t st)
+{
+    k_peer_wait<<<1, MAX_RANKS, 0, st>>>(p, slot_base);
+    return 1;
 }
 
 int launch_count_dead(const StepParams &p, cudaStream_t st)

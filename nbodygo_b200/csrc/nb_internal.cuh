@@ -38,7 +38,7 @@ struct Counters {
     int overflow;                   // pair / host-event capacity exceeded
     int rounds;                     // resolve rounds
     int total_pairs;                // pairs over all ranks (set by resolve)
-    int _pad;
+    int peer_timeout;               // a peer flag wait ran into its time limit
 };
 
 struct DevState {
@@ -59,8 +59,21 @@ struct DevState {
     unsigned *zeros;           // 1024 zeros (opaque low words for the rsqrt seeds in K1)
 };
 
+// Peer replicas of the state arrays K4 updates (mapped through CUDA IPC, or plain UVA pointers when
+// all handles live in one process).  K4 stores the new shard state into every peer over NVLink:
+// the "all-gather" is fused into the integrate kernel.  sync[q] points at rank q's flag block:
+// slots [0,MAX_RANKS) = "arrived(step)" written by each peer, [MAX_RANKS,2*MAX_RANKS) = "done reading(step)".
+struct PeerTable {
+    double *x[MAX_RANKS], *y[MAX_RANKS], *z[MAX_RANKS], *vx[MAX_RANKS], *vy[MAX_RANKS], *vz[MAX_RANKS],
+        *rest[MAX_RANKS];
+    uint8_t *flags[MAX_RANKS];
+    unsigned long long *sync[MAX_RANKS];
+};
+
 struct StepParams {
     DevState s;
+    const PeerTable *peers;      // device pointer, or nullptr (single GPU / NCCL fallback)
+    unsigned long long step_id;  // cycle counter, identical on every rank
     long long n;         // bodies
     long long i0, i1;    // local i-shard
     long long n_pad_local;  // stride of partial-sum slots
@@ -81,6 +94,9 @@ int launch_force(const StepParams &p, cudaStream_t st, int force_R);
 int launch_resolve(const StepParams &p, cudaStream_t st);
 int launch_integrate(const StepParams &p, cudaStream_t st);
 int launch_count_dead(const StepParams &p, cudaStream_t st);
+// peer flag protocol: slot_base 0 = arrived, MAX_RANKS = done reading
+int launch_peer_signal(const StepParams &p, int slot_base, cudaStream_t st);
+int launch_peer_wait(const StepParams &p, int slot_base, cudaStream_t st);
 // stable compaction of !Exists bodies; returns launches. d_map[k] = old index of new body k.
 int launch_compact_map(const DevState &s, long long n, long long *d_map, unsigned *d_block_sums,
                        long long *d_new_n, cudaStream_t st);

@@ -41,10 +41,12 @@ def _rank_main(rank, world, n, steps, q_uid, q_out):
     sim.close()
 
 
+@pytest.mark.parametrize("peer_push", ["1", "0"], ids=["peer-push", "nccl-allgather"])
 @pytest.mark.parametrize("world,n", [(2, 5001), (2, 300)])
-def test_sharded_step_equals_single_gpu(world, n):
+def test_sharded_step_equals_single_gpu(world, n, peer_push, monkeypatch):
     if _ndev() < world:
         pytest.skip(f"needs {world} GPUs")
+    monkeypatch.setenv("NB_PEER_PUSH", peer_push)  # inherited by the spawned ranks
     import torch.multiprocessing as mp
     from nbodygo_b200 import capi
     steps = 3
@@ -109,10 +111,12 @@ def _rank_sync_ops(rank, world, n, q_uid, q_out):
     sim.close()
 
 
-def test_state_sync_ops_on_two_gpus():
+@pytest.mark.parametrize("peer_push", ["1", "0"], ids=["peer-push", "nccl-allgather"])
+def test_state_sync_ops_on_two_gpus(peer_push, monkeypatch):
     world, n = 2, 3001
     if _ndev() < world:
         pytest.skip("needs 2 GPUs")
+    monkeypatch.setenv("NB_PEER_PUSH", peer_push)
     import torch.multiprocessing as mp
     from nbodygo_b200 import capi
     ctx = mp.get_context("spawn")

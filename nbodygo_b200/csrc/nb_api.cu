@@ -97,6 +97,7 @@ struct nb_sim {
     PeerTable *d_peers = nullptr;
     unsigned long long *d_sync = nullptr;  // my flag block: 2*MAX_RANKS slots
     unsigned long long step_id = 0;
+    int2 *pairs_all_base = nullptr;
     std::vector<void *> ipc_opened;
 };
 
@@ -509,8 +510,13 @@ extern "C" int nb_step(nb_handle h, double time_scaling, double R, uint32_t opts
     h->d.pair_counts = h->d_pair_counts;
     p.seg_stride = h->seg_cap;
     p.s = h->d;
-    p.peers = (h->peer_push && !(opts & NB_STEP_NO_INTEGRATE)) ? h->d_peers : nullptr;
     p.step_id = ++h->step_id;
+    p.peers = h->peer_push ? h->d_peers : nullptr;
+    if (h->peer_push) {  // this cycle's parity of the gathered pair buffers
+        const long long par = (long long)(p.step_id & 1ull);
+        p.s.pairs_all = h->pairs_all_base + par * h->nranks * h->seg_cap;
+        p.s.pair_counts = h->d_pair_counts + par * MAX_RANKS;
+    }
 
     NB_CUDA(h, cudaEventRecord(h->ev[0], h->st));
     NB_CUDA(h, cudaMemsetAsync(h->d.ctr, 0, sizeof(Counters), h->st));
@@ -519,8 +525,14 @@ extern "C" int nb_step(nb_handle h, double time_scaling, double R, uint32_t opts
     h->launches += launch_force(p, h->st, h->force_R);
     NB_CUDA(h, cudaEventRecord(h->ev[2], h->st));
     if (h->nranks > 1 && (opts & NB_STEP_COLLISIONS)) {
-        rc = exchange_pairs(h, p);
-        if (rc) return rc;
+        if (h->peer_push) {
+            h->launches += launch_push_pairs(p, h->st);
+            h->launches += launch_peer_signal(p, PEER_SLOT_PAIRS, h->st);
+            h->launches += launch_peer_wait(p, PEER_SLOT_PAIRS, h->st);
+        } else {
+            rc = exchange_pairs(h, p);
+            if (rc) return rc;
+        }
     }
     NB_CUDA(h, cudaEventRecord(h->ev[3], h->st));
     if (opts & NB_STEP_COLLISIONS) h->launches += launch_resolve(p, h->st);
@@ -529,8 +541,8 @@ extern "C" int nb_step(nb_handle h, double time_scaling, double R, uint32_t opts
     if (h->peer_push && advance) {
         // nobody may overwrite my replica before I have finished reading this cycle's inputs (K1, K3),
         // and I may not overwrite a peer's before it has: publish "done reading", wait for everyone's
-        h->launches += launch_peer_signal(p, MAX_RANKS, h->st);
-        h->launches += launch_peer_wait(p, MAX_RANKS, h->st);
+        h->launches += launch_peer_signal(p, PEER_SLOT_DONE, h->st);
+        h->launches += launch_peer_wait(p, PEER_SLOT_DONE, h->st);
     }
     h->launches += launch_integrate(p, h->st);
     NB_CUDA(h, cudaEventRecord(h->ev[5], h->st));
@@ -538,8 +550,8 @@ extern "C" int nb_step(nb_handle h, double time_scaling, double R, uint32_t opts
         if (advance) {
             if (h->peer_push) {
                 // K4 already stored the shard into every peer; wait until every peer's shard has landed here
-                h->launches += launch_peer_signal(p, 0, h->st);
-                h->launches += launch_peer_wait(p, 0, h->st);
+                h->launches += launch_peer_signal(p, PEER_SLOT_ARRIVED, h->st);
+                h->launches += launch_peer_wait(p, PEER_SLOT_ARRIVED, h->st);
             } else {
                 NB_NCCL(h, g_nccl.GroupStart());
                 double *arrs[] = {h->d.x, h->d.y, h->d.z, h->d.vx, h->d.vy, h->d.vz, h->d.rest};
@@ -626,13 +638,16 @@ extern "C" int nb_get_pairs(nb_handle h, int32_t *i, int32_t *j, int64_t cap, in
     if (!h->stepped || !(h->last_opts & NB_STEP_COLLISIONS)) return NB_OK;
     NB_CUDA(h, cudaSetDevice(h->device));
     std::vector<int2> all;
+    if (h->peer_push)  // counts of the last cycle's parity live on the device
+        NB_CUDA(h, cudaMemcpy(h->h_counts, h->last_params.s.pair_counts, h->nranks * sizeof(unsigned long long),
+                              cudaMemcpyDeviceToHost));
     for (int r = 0; r < h->nranks; ++r) {
         unsigned long long c = h->nranks == 1 ? h->h_ctr->n_pairs : h->h_counts[r];
         c = std::min<unsigned long long>(c, (unsigned long long)h->seg_cap);
         if (!c) continue;
         const size_t off = all.size();
         all.resize(off + c);
-        NB_CUDA(h, cudaMemcpy(all.data() + off, h->d.pairs_all + (long long)r * h->last_params.seg_stride,
+        NB_CUDA(h, cudaMemcpy(all.data() + off, h->last_params.s.pairs_all + (long long)r * h->last_params.seg_stride,
                               c * sizeof(int2), cudaMemcpyDeviceToHost));
     }
     std::sort(all.begin(), all.end(), [](const int2 &a, const int2 &b) { return a.x != b.x ? a.x < b.x : a.y < b.y; });
@@ -685,8 +700,8 @@ extern "C" int nb_comm_unique_id(void *id128)
 // agree on the outcome: if any rank cannot map a peer, everybody falls back to the NCCL all-gather.
 namespace {
 struct PeerInfo {
-    cudaIpcMemHandle_t ipc[9];
-    unsigned long long raw[9];
+    cudaIpcMemHandle_t ipc[11];
+    unsigned long long raw[11];
     long long pid;
     int device, ok;
 };
@@ -695,16 +710,27 @@ struct PeerInfo {
 static int setup_peer_push(nb_handle h)
 {
     const int P = h->nranks;
-    NB_CUDA(h, cudaMalloc((void **)&h->d_sync, 2 * MAX_RANKS * sizeof(unsigned long long)));
-    NB_CUDA(h, cudaMemset(h->d_sync, 0, 2 * MAX_RANKS * sizeof(unsigned long long)));
-    void *mine[9] = {h->d.x, h->d.y, h->d.z, h->d.vx, h->d.vy, h->d.vz, h->d.rest, h->d.flags, h->d_sync};
+    NB_CUDA(h, cudaMalloc((void **)&h->d_sync, PEER_SYNC_SLOTS * sizeof(unsigned long long)));
+    NB_CUDA(h, cudaMemset(h->d_sync, 0, PEER_SYNC_SLOTS * sizeof(unsigned long long)));
+    // gathered pair buffers, double-buffered by cycle parity (a fast peer may already be pushing the
+    // next cycle's pairs while this rank's host still reads the last cycle's list)
+    if (h->d.pairs_all != h->d.pairs) cudaFree(h->d.pairs_all);
+    h->d.pairs_all = nullptr;
+    NB_CUDA(h, cudaMalloc((void **)&h->d.pairs_all, (size_t)2 * P * h->seg_cap * sizeof(int2)));
+    cudaFree(h->d_pair_counts);
+    h->d_pair_counts = nullptr;
+    NB_CUDA(h, cudaMalloc((void **)&h->d_pair_counts, 2 * MAX_RANKS * sizeof(unsigned long long)));
+    NB_CUDA(h, cudaMemset(h->d_pair_counts, 0, 2 * MAX_RANKS * sizeof(unsigned long long)));
+    h->pairs_all_base = h->d.pairs_all;
+    void *mine[11] = {h->d.x, h->d.y, h->d.z, h->d.vx, h->d.vy, h->d.vz, h->d.rest, h->d.flags, h->d_sync,
+                      h->d.pairs_all, h->d_pair_counts};
     std::vector<PeerInfo> info((size_t)P);
     PeerInfo &me = info[(size_t)h->rank];
     memset(&me, 0, sizeof me);
     me.ok = 1;
     me.pid = (long long)getpid();
     me.device = h->device;
-    for (int k = 0; k < 9; ++k) {
+    for (int k = 0; k < 11; ++k) {
         me.raw[k] = (unsigned long long)(uintptr_t)mine[k];
         if (cudaIpcGetMemHandle(&me.ipc[k], mine[k]) != cudaSuccess) { me.ok = 0; cudaGetLastError(); }
     }
@@ -723,11 +749,12 @@ static int setup_peer_push(nb_handle h)
     memset(&t, 0, sizeof t);
     int ok = 1;
     for (int q = 0; q < P && ok; ++q) ok = info[(size_t)q].ok;
-    void **slots[9] = {(void **)t.x, (void **)t.y, (void **)t.z, (void **)t.vx, (void **)t.vy, (void **)t.vz,
-                       (void **)t.rest, (void **)t.flags, (void **)t.sync};
+    void **slots[11] = {(void **)t.x, (void **)t.y, (void **)t.z, (void **)t.vx, (void **)t.vy, (void **)t.vz,
+                        (void **)t.rest, (void **)t.flags, (void **)t.sync, (void **)t.pairs_all,
+                        (void **)t.pair_counts};
     for (int q = 0; q < P && ok; ++q) {
         const PeerInfo &pi = info[(size_t)q];
-        for (int k = 0; k < 9 && ok; ++k) {
+        for (int k = 0; k < 11 && ok; ++k) {
             void *ptr = nullptr;
             if (q == h->rank) {
                 ptr = mine[k];
@@ -780,12 +807,16 @@ extern "C" int nb_comm_init(nb_handle h, int rank, int nranks, const void *id128
     h->nranks = nranks;
     // gathered pair list: one segment per rank
     if (nranks > 1) {
-        h->d.pairs_all = nullptr;
-        NB_CUDA(h, cudaMalloc((void **)&h->d.pairs_all, (size_t)h->seg_cap * nranks * sizeof(int2)));
         const char *e = getenv("NB_PEER_PUSH");
         if (!e || atoi(e) != 0) {
             int rc = setup_peer_push(h);
             if (rc != NB_OK) return rc;
+        }
+        if (!h->peer_push) {
+            if (h->d.pairs_all != h->d.pairs) cudaFree(h->d.pairs_all);
+            h->d.pairs_all = nullptr;
+            NB_CUDA(h, cudaMalloc((void **)&h->d.pairs_all, (size_t)h->seg_cap * nranks * sizeof(int2)));
+            h->pairs_all_base = h->d.pairs_all;
         }
     }
     return NB_OK;

@@ -68,7 +68,11 @@ struct PeerTable {
         *rest[MAX_RANKS];
     uint8_t *flags[MAX_RANKS];
     unsigned long long *sync[MAX_RANKS];
+    int2 *pairs_all[MAX_RANKS];               // base of rank q's gathered pair buffer: [2 parities][nranks][seg_cap]
+    unsigned long long *pair_counts[MAX_RANKS];  // base of rank q's counts: [2 parities][MAX_RANKS]
 };
+constexpr int PEER_SLOT_ARRIVED = 0, PEER_SLOT_DONE = MAX_RANKS, PEER_SLOT_PAIRS = 2 * MAX_RANKS;
+constexpr int PEER_SYNC_SLOTS = 3 * MAX_RANKS;
 
 struct StepParams {
     DevState s;
@@ -97,6 +101,8 @@ int launch_count_dead(const StepParams &p, cudaStream_t st);
 // peer flag protocol: slot_base 0 = arrived, MAX_RANKS = done reading
 int launch_peer_signal(const StepParams &p, int slot_base, cudaStream_t st);
 int launch_peer_wait(const StepParams &p, int slot_base, cudaStream_t st);
+// copies this rank's pair list and count into every rank's gathered buffer (this cycle's parity)
+int launch_push_pairs(const StepParams &p, cudaStream_t st);
 // stable compaction of !Exists bodies; returns launches. d_map[k] = old index of new body k.
 int launch_compact_map(const DevState &s, long long n, long long *d_map, unsigned *d_block_sums,
                        long long *d_new_n, cudaStream_t st);

@@ -233,6 +233,30 @@ __global__ void __launch_bounds__(RES_THREADS) k_resolve(const __grid_constant__
     if (tid == 0) s.ctr->rounds = rounds;
 }
 
+// Pair exchange fused over peer memory: every rank stores its list (and count) into the segment
+// [rank] of every rank's gathered buffer — no collective, no host round trip for the counts.
+__global__ void __launch_bounds__(256) k_push_pairs(const __grid_constant__ StepParams p)
+{
+    const PeerTable &pt = *p.peers;
+    const unsigned long long cnt_raw = p.s.ctr->n_pairs;
+    const long long cnt = (long long)(cnt_raw > (unsigned long long)p.seg_cap ? (unsigned long long)p.seg_cap : cnt_raw);
+    const long long par = (long long)(p.step_id & 1ull);
+    const long long seg = (par * p.nranks + p.rank) * p.seg_cap;
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < cnt;
+         k += (long long)gridDim.x * blockDim.x) {
+        const int2 v = p.s.pairs[k];
+        for (int q = 0; q < p.nranks; ++q) pt.pairs_all[q][seg + k] = v;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < p.nranks)
+        pt.pair_counts[threadIdx.x][par * MAX_RANKS + p.rank] = cnt_raw;  // raw: overflow stays visible to all
+}
+
+int launch_push_pairs(const StepParams &p, cudaStream_t st)
+{
+    k_push_pairs<<<64, 256, 0, st>>>(p);
+    return 1;
+}
+
 int launch_resolve(const StepParams &p, cudaStream_t st)
 {
     k_resolve<<<1, RES_THREADS, 0, st>>>(p);

@@ -42,7 +42,7 @@ def _rank_main(rank, world, n, steps, q_uid, q_out):
 
 
 @pytest.mark.parametrize("peer_push", ["1", "0"], ids=["peer-push", "nccl-allgather"])
-@pytest.mark.parametrize("world,n", [(2, 5001), (2, 300)])
+@pytest.mark.parametrize("world,n", [(2, 5001), (2, 300), (4, 4001), (8, 9001), (8, 1000)])
 def test_sharded_step_equals_single_gpu(world, n, peer_push, monkeypatch):
     if _ndev() < world:
         pytest.skip(f"needs {world} GPUs")

@@ -128,12 +128,14 @@ __global__ void __launch_bounds__(TJ) k_prep(StepParams p)
     if (j < p.n) {
         const unsigned fl = p.s.flags[j];
         const double px = p.s.x[j], py = p.s.y[j], pz = p.s.z[j];
-        // a live body at a non-finite position is inert as a j-body (the reference would poison
-        // every force with NaN); as an i-body it still receives NaN and is culled by K4
-        const bool live = (fl & NB_F_EXISTS) != 0 && isfinite(px) && isfinite(py) && isfinite(pz);
+        // a live body at a non-finite (or absurd, |coord| >= 1e150: d2 would overflow) position is
+        // inert as a j-body (the reference would poison every force with NaN); as an i-body it still
+        // receives NaN and is culled by K4
+        const bool live = (fl & NB_F_EXISTS) != 0 && fabs(px) < 1e150 && fabs(py) < 1e150 && fabs(pz) < 1e150;
         if (live) {
             x = px; y = py; z = pz;
             r = p.s.radius[j];
+            if (isnan(r)) r = INFINITY;  // NaN radius: the reference's predicate is never true; screen its whole tile
             if (!(fl & NB_F_FRAGMENTING)) m = p.s.mass[j];
         }
     }

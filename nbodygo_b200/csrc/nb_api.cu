@@ -214,7 +214,7 @@ extern "C" int nb_create(int device, int64_t capacity, int64_t pair_capacity, nb
     NB_TRY(cudaMalloc((void **)&h->d.flags, (size_t)h->cap_pad));
     NB_TRY(cudaMemsetAsync(h->d.behavior, 0, (size_t)h->cap_pad, h->st));
     NB_TRY(cudaMemsetAsync(h->d.flags, 0, (size_t)h->cap_pad, h->st));
-    NB_TRY(cudaMalloc((void **)&h->d.tile_rmax, (size_t)(h->cap_pad / TJ) * sizeof(double)));
+    NB_TRY(cudaMalloc((void **)&h->d.tile_rmax, (size_t)(h->cap_pad / TJ_SMALL) * sizeof(double)));
     NB_TRY(cudaMalloc((void **)&h->d.render, (size_t)h->cap_pad * 3 * sizeof(float)));
     NB_TRY(cudaMalloc((void **)&h->d.render_exists, (size_t)h->cap_pad));
     NB_TRY(cudaMemsetAsync(h->d.render, 0, (size_t)h->cap_pad * 3 * sizeof(float), h->st));
@@ -398,10 +398,13 @@ extern "C" int nb_compact(nb_handle h, int64_t *n_out, int64_t *old_index, int64
 }
 
 // ---------------------------------------------------------------- step
-static void chunking(long long n, int &n_tiles, int &n_chunks, int &tiles_per_chunk)
+static void chunking(long long n, int &tj, int &n_tiles, int &n_chunks, int &tiles_per_chunk)
 {
     // a function of n only: the per-body summation order never depends on the grid or the rank count
-    n_tiles = (int)((n + TJ - 1) / TJ);
+    long long small_below = TJ_SMALL_BELOW;
+    if (const char *e = getenv("NB_TJ_SMALL_BELOW")) small_below = atoll(e);  // development override
+    tj = n < small_below ? TJ_SMALL : TJ_LARGE;
+    n_tiles = (int)((n + tj - 1) / tj);
     // enough chunks that the CTA grid has >= ~40 rounds per SM (tail < ~1 %), within [32, MAX_CHUNKS]
     long long want = n > 0 ? (CHUNK_TARGET_CTAS * 512 + n - 1) / n : 1;
     if (const char *e = getenv("NB_CHUNKS")) want = atoll(e);  // development override (tools/kbench.py)
@@ -493,7 +496,7 @@ extern "C" int nb_step(nb_handle h, double time_scaling, double R, uint32_t opts
     NB_CUDA(h, cudaSetDevice(h->device));
     StepParams p{};
     p.n = h->n;
-    chunking(h->n, p.n_tiles, p.n_chunks, p.tiles_per_chunk);
+    chunking(h->n, p.tj, p.n_tiles, p.n_chunks, p.tiles_per_chunk);
     const long long shard = (h->n + h->nranks - 1) / h->nranks;
     p.i0 = std::min<long long>(h->n, (long long)h->rank * shard);
     p.i1 = std::min<long long>(h->n, p.i0 + shard);
@@ -841,8 +844,8 @@ extern "C" int nb_plan(int64_t n, int rank, int nranks, int64_t *i0, int64_t *i1
     const long long a = std::min<long long>(n, (long long)rank * shard);
     if (i0) *i0 = a;
     if (i1) *i1 = std::min<long long>(n, a + shard);
-    int nt, nc, tpc;
-    chunking(n, nt, nc, tpc);
+    int tj, nt, nc, tpc;
+    chunking(n, tj, nt, nc, tpc);
     if (n_chunks) *n_chunks = nc;
     if (tiles_per_chunk) *tiles_per_chunk = tpc;
     return NB_OK;

@@ -121,6 +121,7 @@ __device__ __forceinline__ double w_from_seed(double y0, double d2, double mj)
 // j-filter of body.go:162-165 folded into the mass); bodies that do not exist — and the tail of
 // the last tile — are parked massless at a far, finite position so they are never screened.
 // Also the per-tile max radius of live bodies.
+template <int TJ>
 __global__ void __launch_bounds__(TJ) k_prep(StepParams p)
 {
     const long long j = (long long)blockIdx.x * TJ + threadIdx.x;
@@ -160,7 +161,8 @@ __global__ void __launch_bounds__(TJ) k_prep(StepParams p)
 int launch_prep(const StepParams &p, cudaStream_t st)
 {
     if (p.n_tiles <= 0) return 0;
-    k_prep<<<p.n_tiles, TJ, 0, st>>>(p);
+    if (p.tj == TJ_SMALL) k_prep<TJ_SMALL><<<p.n_tiles, TJ_SMALL, 0, st>>>(p);
+    else k_prep<TJ_LARGE><<<p.n_tiles, TJ_LARGE, 0, st>>>(p);
     return 1;
 }
 
@@ -219,7 +221,7 @@ __device__ __noinline__ double exact_pair(const StepParams &p, long long i, long
 // ---------------------------------------------------------------- K1: fast pass over one tile
 // Two j-bodies per iteration (LDS.128), R i-bodies per thread.  SELF: the tile holds bodies of this
 // CTA; the pair (i,i) gets the seed 0 (hence w == 0 exactly) and is left out of the minimum.
-template <int R, int UNR, bool SELF>
+template <int R, int UNR, bool SELF, int TJ>
 __device__ __forceinline__ void fast_tile(const double *sx, const double *sy, const double *sz, const double *sj,
                                           const double (&xi)[R], const double (&yi)[R], const double (&zi)[R],
                                           const unsigned (&zlo)[2 * R], const int (&self_j)[R], double (&tx)[R],
@@ -263,7 +265,7 @@ __device__ __forceinline__ void fast_tile(const double *sx, const double *sy, co
 
 // ---------------------------------------------------------------- K1: kernel
 // UNR = unroll of the j-group loop (each group is two j-bodies).
-template <int R, int NT, int MINB, int UNR>
+template <int R, int NT, int MINB, int UNR, int TJ>
 __global__ void __launch_bounds__(NT, MINB) k_force(const __grid_constant__ StepParams p)
 {
     static_assert(TJ % 2 == 0 && R <= 16, "tile of j-pairs");
@@ -352,12 +354,12 @@ __global__ void __launch_bounds__(NT, MINB) k_force(const __grid_constant__ Step
             int self_j[R];
 #pragma unroll
             for (int r = 0; r < R; ++r) self_j[r] = (int)(ibase + (long long)r * NT + tid - jt0);
-            fast_tile<R, UNR, true>(sx, sy, sz, sj, xi, yi, zi, zlo, self_j, tx, ty, tz, lo);
+            fast_tile<R, UNR, true, TJ>(sx, sy, sz, sj, xi, yi, zi, zlo, self_j, tx, ty, tz, lo);
         } else {
             int self_j[R];
 #pragma unroll
             for (int r = 0; r < R; ++r) self_j[r] = -1;
-            fast_tile<R, UNR, false>(sx, sy, sz, sj, xi, yi, zi, zlo, self_j, tx, ty, tz, lo);
+            fast_tile<R, UNR, false, TJ>(sx, sy, sz, sj, xi, yi, zi, zlo, self_j, tx, ty, tz, lo);
         }
 
         // ---- commit, or (rare) redo the tile carefully for a body that saw a screened pair.
@@ -422,7 +424,8 @@ static int launch_force_t(const StepParams &p, cudaStream_t st)
     const long long n_local = p.i1 - p.i0;
     const long long per = (long long)NT * R;
     dim3 grid((unsigned)((n_local + per - 1) / per), (unsigned)p.n_chunks);
-    k_force<R, NT, MINB, UNR><<<grid, NT, 0, st>>>(p);
+    if (p.tj == TJ_SMALL) k_force<R, NT, MINB, UNR, TJ_SMALL><<<grid, NT, 0, st>>>(p);
+    else k_force<R, NT, MINB, UNR, TJ_LARGE><<<grid, NT, 0, st>>>(p);
     return 1;
 }
 

@@ -18,7 +18,12 @@
 
 namespace nb {
 
-constexpr int TJ = 256;      // bodies per j-tile (one bulk copy of 2 KB per field)
+// bodies per j-tile (one TMA bulk copy per field and tile).  Small collections use small tiles so
+// that the sweep has enough independent (i-block, j-chunk) work items; the choice is a function of
+// n only (chunking() in nb_api.cu), like everything that fixes the per-body summation order.
+constexpr int TJ_LARGE = 256, TJ_SMALL = 64;
+constexpr long long TJ_SMALL_BELOW = 16384;  // n < this uses TJ_SMALL
+constexpr int TJ = TJ_LARGE;                 // allocation granularity
 constexpr int NSTAGE = 2;    // smem stages of the j pipeline
 // j-chunks per body (= partial-sum slots; a function of n only, see chunking() in nb_api.cu)
 constexpr int MIN_CHUNKS = 32;
@@ -81,7 +86,8 @@ struct StepParams {
     long long n;         // bodies
     long long i0, i1;    // local i-shard
     long long n_pad_local;  // stride of partial-sum slots
-    int n_tiles;         // ceil(n / TJ)
+    int tj;              // tile size of this cycle: TJ_SMALL or TJ_LARGE
+    int n_tiles;         // ceil(n / tj)
     int n_chunks;        // S
     int tiles_per_chunk;
     int rank, nranks;

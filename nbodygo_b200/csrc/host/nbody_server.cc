@@ -4,7 +4,9 @@
 // (cmd/server/main.go:113-236): --sim-name/-n, --sim-args/-a, --collision/-c, --bodies/-b,
 // --threads/-t (accepted, no-op), --scaling/-m, --csv/-f, --run-millis/-u, --no-render/-r
 // (always on: there is no renderer here), --no-barnes-hut (always brute force).
-// Additions: --gpu=<device>, --seed=<n>, --iterations=<n>, --dump-csv=<path>.
+// Additions: --gpu=<device>, --seed=<n>, --iterations=<n>, --dump-csv=<path> (initial bodies),
+// --dump-final-csv=<path> (surviving bodies after the run: a restartable checkpoint, the reference
+// has none).
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -16,7 +18,7 @@ using namespace nbodygo;
 
 int main(int argc, char **argv)
 {
-    std::string simName = "Sim1", simArgs, csvPath, dumpCsv;
+    std::string simName = "Sim1", simArgs, csvPath, dumpCsv, dumpFinalCsv;
     CollisionBehavior behavior = Elastic;
     BodyColor color = Random;
     int bodyCount = 1000, runMillis = -1, iterations = 0, device = 0;
@@ -48,6 +50,7 @@ int main(int argc, char **argv)
         else if (a == "--seed") seed = std::strtoull(val().c_str(), nullptr, 10);
         else if (a == "--iterations") iterations = std::atoi(val().c_str());
         else if (a == "--dump-csv") dumpCsv = val();
+        else if (a == "--dump-final-csv") dumpFinalCsv = val();
         else {
             std::fprintf(stderr, "unknown option %s\n", a.c_str());
             return 2;
@@ -70,6 +73,12 @@ int main(int argc, char **argv)
     try {
         const HeadlessResult r = RunHeadless(bodies, scaling, runMillis, iterations, device, false);
         std::printf("bodies: %zu -> %d\ninteractions/s: %.6e\n", bodies.size(), r.finalBodies, r.interactionsPerSec);
+        if (!dumpFinalCsv.empty()) {
+            std::vector<BodyPtr> alive;
+            for (auto &b : bodies)
+                if (b->Exists) alive.push_back(b);
+            WriteCsv(dumpFinalCsv, alive);
+        }
     } catch (const std::exception &e) {
         std::fprintf(stderr, "%s\n", e.what());
         return 1;

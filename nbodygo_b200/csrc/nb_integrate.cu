@@ -124,7 +124,7 @@ __global__ void k_peer_signal(const __grid_constant__ StepParams p, int slot_bas
 }
 
 // One thread per peer: wait until every peer has published >= step_id in my flag block.  Bounded
-// (20 s of globaltimer) so that a lost peer turns into an error flag, never into a hung GPU.
+// (60 s of globaltimer) so that a lost peer turns into an error flag, never into a hung GPU.
 __global__ void k_peer_wait(const __grid_constant__ StepParams p, int slot_base)
 {
     const int q = threadIdx.x;
@@ -135,7 +135,7 @@ __global__ void k_peer_wait(const __grid_constant__ StepParams p, int slot_base)
         while (*f < p.step_id) {
             __nanosleep(200);
             asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-            if (t1 - t0 > 20000000000ull) {
+            if (t1 - t0 > 60000000000ull) {
                 p.s.ctr->peer_timeout = 1;
                 break;
             }

@@ -169,8 +169,11 @@ int nb_get_forces(nb_handle h, double *fx, double *fy, double *fz);
  * (i asc, j asc) — the single-worker arrival order of the reference.
  * *n receives the total; at most cap are written. */
 int nb_get_pairs(nb_handle h, int32_t *i, int32_t *j, int64_t cap, int64_t *n);
-/* Subsume / fragment (and, with NB_STEP_NO_RESOLVE, collision) records of the
- * last step, sorted by (kind, a, b). */
+/* Subsume / fragment records of the last step, sorted by (kind, a, b).  (With
+ * NB_STEP_NO_RESOLVE the unresolved collision events are the pair list of
+ * nb_get_pairs.)  On several GPUs the subsume records cover the handle's own
+ * i-range — merge the handles' lists — while the fragment records come from the
+ * replicated resolve and are identical on every handle: take them from one. */
 int nb_get_host_events(nb_handle h, nb_event *ev, int64_t cap, int64_t *n);
 
 /* ---- multi-GPU (one handle per GPU, one process per GPU or one process) - */

@@ -163,6 +163,12 @@ int nb_download_state(nb_handle h,
 /* Renderable snapshot of the last step (cmd/body/renderable.go:22-40):
  * xyz = 3 floats per body (zeros for !Exists stubs), exists = 1 byte per body. */
 int nb_download_render(nb_handle h, float *xyz, uint8_t *exists);
+/* Zero-copy variant for the per-cycle render path: returns two library-owned pinned
+ * host buffers (capacity-sized; C memory, so no Go pointer is retained) that EVERY
+ * subsequent nb_step fills with the snapshot as part of the cycle's own stream —
+ * valid from the return of nb_step / nb_sync until the next step.  Replaces the
+ * per-body Renderable allocation of computation-runner.go:317-320. */
+int nb_render_buffers(nb_handle h, float **xyz, uint8_t **exists);
 /* Force accumulated on each body in the last step (Body.fx,fy,fz). */
 int nb_get_forces(nb_handle h, double *fx, double *fy, double *fz);
 /* Elastic collision events of the last step as ordered pairs, sorted by

@@ -28,7 +28,7 @@ EV_COLLISION, EV_SUBSUME, EV_FRAGMENT = 0, 1, 2
 # every symbol include/nbody_b200.h declares (checked by tests/test_capi_symbols.py)
 SYMBOLS = (
     "nb_create", "nb_destroy", "nb_last_error", "nb_abi_version", "nb_upload", "nb_patch", "nb_append",
-    "nb_compact", "nb_count", "nb_step", "nb_sync", "nb_download_state", "nb_download_render",
+    "nb_compact", "nb_count", "nb_step", "nb_sync", "nb_download_state", "nb_download_render", "nb_render_buffers",
     "nb_get_forces", "nb_get_pairs", "nb_get_host_events", "nb_comm_unique_id", "nb_comm_init",
     "nb_shard_range", "nb_plan", "nb_measure_fp64_peak", "nb_launch_count",
 )
@@ -84,6 +84,7 @@ def load(path: str | None = None):
     L.nb_sync.argtypes = [H, C.POINTER(StepResult)]
     L.nb_download_state.argtypes = [H] + [_DP] * 9 + [_U8P] * 2
     L.nb_download_render.argtypes = [H, C.POINTER(C.c_float), _U8P]
+    L.nb_render_buffers.argtypes = [H, C.POINTER(C.POINTER(C.c_float)), C.POINTER(_U8P)]
     L.nb_get_forces.argtypes = [H, _DP, _DP, _DP]
     L.nb_get_pairs.argtypes = [H, _I32P, _I32P, C.c_int64, _I64P]
     L.nb_get_host_events.argtypes = [H, C.c_void_p, C.c_int64, _I64P]
@@ -206,6 +207,15 @@ class Sim:
         exists = np.zeros(n, dtype=np.uint8) if exists is None else exists
         self._chk(self.L.nb_download_render(self.h, xyz.ctypes.data_as(C.POINTER(C.c_float)), _p(exists, _U8P)))
         return xyz, exists
+
+    def render_buffers(self):
+        """Library-owned pinned (xyz[cap,3] float32, exists[cap] uint8) views filled by every step."""
+        px, pe = C.POINTER(C.c_float)(), _U8P()
+        self._chk(self.L.nb_render_buffers(self.h, C.byref(px), C.byref(pe)))
+        cap = self.capacity
+        xyz = np.ctypeslib.as_array(px, shape=(cap, 3))
+        ex = np.ctypeslib.as_array(pe, shape=(cap,))
+        return xyz, ex
 
     def forces(self):
         n = self.count()

@@ -16,6 +16,8 @@ GpuStepper::GpuStepper(int device, int64_t capacity) : cap_(capacity)
         // no CPU fallback by design: the caller must not silently continue on the host
         throw std::runtime_error(std::string("[ERROR] nb_create: ") + nb_last_error(nullptr));
     }
+    // the per-cycle Renderable snapshot lands in pinned host memory as part of the cycle itself
+    if (nb_render_buffers(h_, &pinXyz_, &pinExists_) != NB_OK) { pinXyz_ = nullptr; pinExists_ = nullptr; }
 }
 
 GpuStepper::~GpuStepper()
@@ -106,22 +108,28 @@ bool GpuStepper::Step(BodyCollection &bc, double timeScaling, double R, ResultQu
     hostStale_ = true;
     // Renderables from the float32 snapshot (13 B/body) — computation-runner.go:317-320
     grow(n);
-    if (n > 0 && nb_download_render(h_, xyz.data(), exists.data()) != NB_OK) {
-        std::fprintf(stderr, "[ERROR] nb_download_render: %s\n", nb_last_error(h_));
-        return false;
+    const float *rxyz = pinXyz_;
+    const uint8_t *rex = pinExists_;
+    if (!rxyz) {  // fallback: explicit copy
+        if (n > 0 && nb_download_render(h_, xyz.data(), exists.data()) != NB_OK) {
+            std::fprintf(stderr, "[ERROR] nb_download_render: %s\n", nb_last_error(h_));
+            return false;
+        }
+        rxyz = xyz.data();
+        rex = exists.data();
     }
     rq.queue.reserve(n);
     for (size_t i = 0; i < n; ++i) {
         Body &b = *arr[i];
         Renderable r;
         r.Id = b.Id;
-        if (b.Exists && !exists[i]) {
+        if (b.Exists && !rex[i]) {
             std::fprintf(stderr, "[ERROR] NaN values. id=%d (removing from sim)\n", b.Id);  // body.go:135
             b.Exists = false;
         }
         if (b.Exists) {
             r.Exists = true;
-            r.X = xyz[3 * i]; r.Y = xyz[3 * i + 1]; r.Z = xyz[3 * i + 2];
+            r.X = rxyz[3 * i]; r.Y = rxyz[3 * i + 1]; r.Z = rxyz[3 * i + 2];
             r.Radius = b.Radius; r.IsSun = b.IsSun; r.Intensity = (float)b.intensity; r.Color = b.Color;
         }
         rq.Add(r);

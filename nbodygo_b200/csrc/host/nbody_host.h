@@ -210,6 +210,8 @@ private:
     std::vector<double> x, y, z, vx, vy, vz, mass, radius, rest, ff, fs;
     std::vector<uint8_t> beh, flags, exists;
     std::vector<float> xyz;
+    float *pinXyz_ = nullptr;        // library-owned pinned snapshot buffers (nb_render_buffers)
+    uint8_t *pinExists_ = nullptr;
     StepStats stats_;
 };
 

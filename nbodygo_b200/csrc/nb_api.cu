@@ -99,6 +99,9 @@ struct nb_sim {
     unsigned long long step_id = 0;
     int2 *pairs_all_base = nullptr;
     std::vector<void *> ipc_opened;
+    // library-owned pinned host buffers that every step fills with the Renderable snapshot
+    float *h_render = nullptr;
+    uint8_t *h_render_exists = nullptr;
 };
 
 #define NB_CUDA(h, call)                                                                              \
@@ -160,6 +163,8 @@ static void free_all(nb_handle h)
     if (h->h_ctr) cudaFreeHost(h->h_ctr);
     if (h->h_counts) cudaFreeHost(h->h_counts);
     if (h->h_new_n) cudaFreeHost(h->h_new_n);
+    if (h->h_render) cudaFreeHost(h->h_render);
+    if (h->h_render_exists) cudaFreeHost(h->h_render_exists);
     for (auto &e : h->ev) if (e) cudaEventDestroy(e);
     if (h->st) cudaStreamDestroy(h->st);
     delete h;
@@ -569,6 +574,12 @@ extern "C" int nb_step(nb_handle h, double time_scaling, double R, uint32_t opts
         h->launches += launch_count_dead(p, h->st);
     }
     NB_CUDA(h, cudaEventRecord(h->ev[6], h->st));
+    if (h->h_render && h->n > 0) {  // snapshot rides the same stream: in host memory when the step is synced
+        NB_CUDA(h, cudaMemcpyAsync(h->h_render, h->d.render, (size_t)h->n * 3 * sizeof(float), cudaMemcpyDeviceToHost,
+                                   h->st));
+        NB_CUDA(h, cudaMemcpyAsync(h->h_render_exists, h->d.render_exists, (size_t)h->n, cudaMemcpyDeviceToHost,
+                                   h->st));
+    }
     NB_CUDA(h, cudaMemcpyAsync(h->h_ctr, h->d.ctr, sizeof(Counters), cudaMemcpyDeviceToHost, h->st));
     NB_CUDA(h, cudaGetLastError());
     h->pending = true;
@@ -616,6 +627,21 @@ extern "C" int nb_download_render(nb_handle h, float *xyz, uint8_t *exists)
     rc = copy_out(h, exists, h->d.render_exists, (size_t)h->n);
     if (rc) return rc;
     NB_CUDA(h, cudaStreamSynchronize(h->st));
+    return NB_OK;
+}
+
+extern "C" int nb_render_buffers(nb_handle h, float **xyz, uint8_t **exists)
+{
+    if (!h || !xyz || !exists) return NB_ERR_INVALID;
+    NB_CUDA(h, cudaSetDevice(h->device));
+    if (!h->h_render) {
+        NB_CUDA(h, cudaMallocHost((void **)&h->h_render, (size_t)h->cap_pad * 3 * sizeof(float)));
+        NB_CUDA(h, cudaMallocHost((void **)&h->h_render_exists, (size_t)h->cap_pad));
+        memset(h->h_render, 0, (size_t)h->cap_pad * 3 * sizeof(float));
+        memset(h->h_render_exists, 0, (size_t)h->cap_pad);
+    }
+    *xyz = h->h_render;
+    *exists = h->h_render_exists;
     return NB_OK;
 }
 

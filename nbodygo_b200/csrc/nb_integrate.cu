@@ -100,11 +100,18 @@ int launch_integrate(const StepParams &p, cudaStream_t st)
     return 1;
 }
 
-// multi-GPU: after the state exchange every rank counts the dead bodies of the whole array
+// multi-GPU: after the state exchange every rank holds the whole new state; it counts the dead bodies
+// and takes the Renderable snapshot (NewRenderable) of ALL bodies, not only of its own shard
 __global__ void __launch_bounds__(INT_THREADS) k_count_dead(const __grid_constant__ StepParams p)
 {
     const long long i = (long long)blockIdx.x * INT_THREADS + threadIdx.x;
     const int dead = (i < p.n && !(p.s.flags[i] & NB_F_EXISTS)) ? 1 : 0;
+    if (i < p.n) {
+        p.s.render_exists[i] = dead ? 0 : 1;
+        p.s.render[3 * i + 0] = dead ? 0.0f : (float)p.s.x[i];
+        p.s.render[3 * i + 1] = dead ? 0.0f : (float)p.s.y[i];
+        p.s.render[3 * i + 2] = dead ? 0.0f : (float)p.s.z[i];
+    }
     const unsigned dm = __ballot_sync(0xffffffffu, dead);
     if ((threadIdx.x & 31) == 0 && dm) atomicAdd(&p.s.ctr->n_dead, (unsigned long long)__popc(dm));
 }

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define NB_ABI_VERSION 1
+#define NB_ABI_VERSION 2
 
 /* ---- error codes ------------------------------------------------------- */
 #define NB_OK 0
@@ -69,25 +69,31 @@ typedef struct nb_sim *nb_handle;
 typedef struct {
     int64_t n_bodies;       /* bodies in the array                                  */
     int64_t n_pairs;        /* ordered elastic pairs (i,j) detected, all ranks      */
-    int64_t n_host_events;  /* subsume / fragment records handed to the host        */
+    int64_t n_host_events;  /* subsume / fragment records reported to the host      */
     int64_t n_resolved;     /* events for which doElastic ran                       */
     int64_t n_culled;       /* bodies whose Exists was cleared by the NaN cull      */
     int64_t n_dead;         /* bodies with Exists == false after the step           */
+    int64_t n_subsumed;     /* bodies swallowed by ResolveSubsume in this step      */
     int32_t resolve_rounds; /* dependency rounds the resolve kernel needed          */
     int32_t pair_overflow;  /* 1: pair/event capacity exceeded, state NOT advanced  */
     /* device timings of the last step, milliseconds (CUDA events) */
     float ms_total, ms_prep, ms_force, ms_exchange, ms_resolve, ms_integrate;
 } nb_step_result;
 
-/* Event kinds handed back to the host (cmd/body/event.go:20-24). */
-#define NB_EV_COLLISION 0 /* only with NB_STEP_NO_RESOLVE                           */
-#define NB_EV_SUBSUME 1   /* a subsumes b (larger radius first), body.go:178-184    */
+/* Event kinds reported to the host (cmd/body/event.go:20-24).  The device resolves
+ * the whole event queue itself, in the reference's order (BodyCollection.ProcessMods,
+ * cmd/body/body_collection.go:212-233): elastic collisions, ResolveSubsume (mass,
+ * Exists) and the `fragmenting` flag of initiateFragmentation.  The records tell the
+ * host what happened so that it can log, keep its own Body objects in step and do
+ * the host-only part (fragInfo + spawning fragments, cmd/body/fragcalc.go:84-117). */
+#define NB_EV_COLLISION 0 /* reserved                                               */
+#define NB_EV_SUBSUME 1   /* a subsumed b (larger radius first), body.go:178-184,228-244 */
 #define NB_EV_FRAGMENT 2  /* shouldFragment said yes: f1/f2 = thisFactor/otherFactor */
 
 typedef struct {
     int32_t kind;
-    int32_t a, b; /* array indices of b1, b2 */
-    int32_t _pad;
+    int32_t a, b;    /* array indices of b1, b2 */
+    int32_t applied; /* 1: the device applied it; 0: reported only (NB_STEP_NO_RESOLVE / NO_INTEGRATE) */
     double dist; /* centre distance (subsume / collision) */
     double f1, f2;
 } nb_event;

@@ -43,6 +43,7 @@ class NbError(RuntimeError):
 class StepResult(C.Structure):
     _fields_ = [("n_bodies", C.c_int64), ("n_pairs", C.c_int64), ("n_host_events", C.c_int64),
                 ("n_resolved", C.c_int64), ("n_culled", C.c_int64), ("n_dead", C.c_int64),
+                ("n_subsumed", C.c_int64),
                 ("resolve_rounds", C.c_int32), ("pair_overflow", C.c_int32),
                 ("ms_total", C.c_float), ("ms_prep", C.c_float), ("ms_force", C.c_float),
                 ("ms_exchange", C.c_float), ("ms_resolve", C.c_float), ("ms_integrate", C.c_float)]
@@ -51,7 +52,7 @@ class StepResult(C.Structure):
         return {f: getattr(self, f) for f, _ in self._fields_}
 
 
-EVENT_DTYPE = np.dtype([("kind", "<i4"), ("a", "<i4"), ("b", "<i4"), ("_pad", "<i4"),
+EVENT_DTYPE = np.dtype([("kind", "<i4"), ("a", "<i4"), ("b", "<i4"), ("applied", "<i4"),
                         ("dist", "<f8"), ("f1", "<f8"), ("f2", "<f8")])
 
 _DP = C.POINTER(C.c_double)

@@ -353,7 +353,7 @@ bool BodyCollection::HandleModBody()
 }
 
 // ---------------------------------------------------------------- ResultQueueHolder
-ResultQueueHolder::ResultQueueHolder(int maxQueues) : maxQueues_(maxQueues), physCap_(maxQueues) {}
+ResultQueueHolder::ResultQueueHolder(int maxQueues) : maxQueues_(maxQueues), physCap_(maxQueues + 1) {}
 
 std::pair<ResultQueuePtr, bool> ResultQueueHolder::NewResultQueue()
 {
@@ -399,8 +399,11 @@ bool ResultQueueHolder::Resize(int maxQueues)
 {
     std::lock_guard<std::mutex> g(lock_);
     if (maxQueues == maxQueues_) return false;
-    // shrinking below the current content keeps the physical room (+1 for the cycle in flight)
-    physCap_ = maxQueues < (int)ch_.size() ? maxQueues_ + 1 : maxQueues;
+    // Physical room always covers the current content plus the one queue a concurrent
+    // NewResultQueue may already have granted (the cycle in flight).  The reference only adds that
+    // slack when shrinking *below* the content (resultqueue.go:176-182); shrinking to exactly the
+    // content (maxQueues == curLen) leaves none and its Add then dies with "No queue capacity".
+    physCap_ = std::max(maxQueues, (int)ch_.size()) + 1;
     maxQueues_ = maxQueues;
     return true;
 }

@@ -1,4 +1,5 @@
 // host_runner.cc — GpuStepper (the C++ twin of the cgo shim) and ComputationRunner.
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -88,10 +89,18 @@ bool GpuStepper::Step(BodyCollection &bc, double timeScaling, double R, ResultQu
 {
     auto &arr = bc.GetArray();
     // fragmenting bodies spawn their fragments on the host, as Body.Compute does (body.go:152-155)
-    for (auto &b : arr) {
-        if (b->Exists && b->fragmenting) {
-            b->fragment(bc);
-            if (!b->Exists) dirty_ = true;
+    const bool inStep = !dirty_ && (int64_t)arr.size() == n_;
+    for (size_t i = 0; i < arr.size(); ++i) {
+        Body &b = *arr[i];
+        if (b.Exists && b.fragmenting) {
+            b.fragment(bc);
+            if (!b.Exists && inStep) {  // fully fragmented (fragcalc.go:114-116): one flag byte to the device
+                const uint8_t fl1 = flagsOf(b);
+                if (nb_patch(h_, (int64_t)i, 1, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                             nullptr, nullptr, nullptr, nullptr, &fl1) != NB_OK)
+                    dirty_ = true;
+                stats_.patches++;
+            }
         }
     }
     if (dirty_ || (int64_t)arr.size() != n_) upload(bc);
@@ -106,8 +115,46 @@ bool GpuStepper::Step(BodyCollection &bc, double timeScaling, double R, ResultQu
     stats_.steps++;
     stats_.ms_device += res.ms_total;
     hostStale_ = true;
-    // Renderables from the float32 snapshot (13 B/body) — computation-runner.go:317-320
     grow(n);
+    // The device resolved the whole event queue in the reference's order (ProcessMods): elastic
+    // collisions, ResolveSubsume and the `fragmenting` flag.  The records keep the host objects in
+    // step: a subsume is mirrored from the device's masses, a fragment decision runs the reference's
+    // own handler for the host-only part (fragInfo).  Nothing is written back to the device.
+    if (res.n_host_events > 0) {
+        std::vector<nb_event> ev((size_t)res.n_host_events);
+        int64_t m = 0;
+        nb_get_host_events(h_, ev.data(), (int64_t)ev.size(), &m);
+        bool anyFragment = false, anySubsume = false;
+        for (int64_t k = 0; k < m; ++k) {
+            anyFragment |= ev[(size_t)k].kind == NB_EV_FRAGMENT;
+            anySubsume |= ev[(size_t)k].kind == NB_EV_SUBSUME && ev[(size_t)k].applied;
+        }
+        if (anyFragment) SyncToHost(bc);  // initiateFragmentation records the body's current position
+        if (anySubsume &&
+            nb_download_state(h_, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, mass.data(), nullptr, nullptr,
+                              nullptr, flags.data()) != NB_OK) {
+            std::fprintf(stderr, "[ERROR] nb_download_state: %s\n", nb_last_error(h_));
+            return false;
+        }
+        for (int64_t k = 0; k < m; ++k) {
+            const nb_event &e = ev[(size_t)k];
+            if (e.a < 0 || e.b < 0 || (size_t)e.a >= n || (size_t)e.b >= n) continue;
+            if (e.kind == NB_EV_SUBSUME && e.applied) {
+                Body &a = *arr[(size_t)e.a], &b = *arr[(size_t)e.b];
+                if (b.Exists && !(flags[(size_t)e.b] & NB_F_EXISTS))  // body.go:243
+                    std::fprintf(stderr, "[INFO] Body ID %d (mass %g) subsumed ID %d (mass %g)\n", a.Id, a.Mass, b.Id, b.Mass);
+                a.Mass = mass[(size_t)e.a];
+                b.Mass = mass[(size_t)e.b];
+                if (!(flags[(size_t)e.a] & NB_F_EXISTS)) a.Exists = false;
+                if (!(flags[(size_t)e.b] & NB_F_EXISTS)) b.Exists = false;
+                stats_.subsumes++;
+            } else if (e.kind == NB_EV_FRAGMENT) {
+                bc.Enqueue(newFragment(arr[(size_t)e.a], arr[(size_t)e.b], e.f1, e.f2));
+            }
+        }
+        if (anyFragment) bc.ProcessMods();
+    }
+    // Renderables from the float32 snapshot (13 B/body) — computation-runner.go:317-320
     const float *rxyz = pinXyz_;
     const uint8_t *rex = pinExists_;
     if (!rxyz) {  // fallback: explicit copy
@@ -134,21 +181,6 @@ bool GpuStepper::Step(BodyCollection &bc, double timeScaling, double R, ResultQu
         }
         rq.Add(r);
     }
-    // subsume / fragment decisions go through the reference's own handlers (ProcessMods)
-    if (res.n_host_events > 0) {
-        std::vector<nb_event> ev((size_t)res.n_host_events);
-        int64_t m = 0;
-        nb_get_host_events(h_, ev.data(), (int64_t)ev.size(), &m);
-        SyncToHost(bc);
-        for (int64_t k = 0; k < m; ++k) {
-            const nb_event &e = ev[(size_t)k];
-            if (e.a < 0 || e.b < 0 || (size_t)e.a >= n || (size_t)e.b >= n) continue;
-            if (e.kind == NB_EV_SUBSUME) bc.Enqueue(newSubsume(arr[e.a], arr[e.b]));
-            else if (e.kind == NB_EV_FRAGMENT) bc.Enqueue(newFragment(arr[e.a], arr[e.b], e.f1, e.f2));
-        }
-        bc.ProcessMods();
-        dirty_ = true;  // masses / Exists / fragmenting changed on the host
-    }
     return true;
 }
 
@@ -159,10 +191,10 @@ void GpuStepper::AfterCycle(BodyCollection &bc, bool arrayChanged, int64_t newCo
     if (!arrayChanged || dirty_) return;
     auto &arr = bc.GetArray();
     int64_t n_dev = n_;
-    if (stats_.last.n_dead > 0) {
-        if (nb_compact(h_, &n_dev, nullptr, 0) != NB_OK) { dirty_ = true; return; }
-        stats_.compacts++;
-    }
+    // deaths (NaN cull on the device, subsume / delete patched from the host) are compacted on the
+    // device exactly like Cycle compacted the host array; a no-op pass when nothing died
+    if (nb_compact(h_, &n_dev, nullptr, 0) != NB_OK) { dirty_ = true; return; }
+    if (n_dev != n_) stats_.compacts++;
     const int64_t adds = newCount - n_dev;
     if (adds < 0 || newCount > cap_) { dirty_ = true; return; }
     if (adds > 0) {
@@ -326,11 +358,11 @@ void ComputationRunner::PrintStats()
     const StepStats &s = stepper_->stats();
     std::printf("Runner\n workerCnt: %d (GPU path: no worker pool)\n iterations: %llu\n computations: %llu\n"
                 " skipped (no queue capacity): %llu\n device ms/computation: %g\n frames per second: %g\n"
-                " elapsed time: %gs\nGpuStepper\n uploads: %llu appends: %llu compacts: %llu downloads: %llu\n",
+                " elapsed time: %gs\nGpuStepper\n uploads: %llu appends: %llu compacts: %llu downloads: %llu patches: %llu subsumes: %llu\n",
                 workerCnt_, (unsigned long long)iterations_, (unsigned long long)computations_,
                 (unsigned long long)skipped_, s.steps ? s.ms_device / (double)s.steps : 0.0, fps, totalMillis / 1000,
                 (unsigned long long)s.uploads, (unsigned long long)s.appends, (unsigned long long)s.compacts,
-                (unsigned long long)s.downloads);
+                (unsigned long long)s.downloads, (unsigned long long)s.patches, (unsigned long long)s.subsumes);
 }
 
 }  // namespace nbodygo

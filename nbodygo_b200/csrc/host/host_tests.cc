@@ -388,7 +388,7 @@ static void TestSubsumeAndFragmentLoop()
     ResultQueueHolder rqh(100);
     ComputationRunner cr(1, 1e-12, false, &rqh, &bc);
     cr.runOneComputation();
-    CHECK(!bodies[1]->Exists && bodies[0]->Mass == 9e20 + 1e10);       // ResolveSubsume on the host
+    CHECK(!bodies[1]->Exists && bodies[0]->Mass == 9e20 + 1e10);       // ResolveSubsume on the device, mirrored to the host objects
     CHECK(bodies[3]->fragmenting);                                       // shouldFragment on the device
     CHECK(bc.Count() == 3);
     for (int k = 0; k < 4; ++k) cr.runOneComputation();

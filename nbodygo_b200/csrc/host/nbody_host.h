@@ -184,7 +184,7 @@ private:
 // ---------------------------------------------------------------- GPU stepper (replaces WorkPool)
 struct StepStats {
     nb_step_result last{};
-    uint64_t steps = 0, uploads = 0, appends = 0, compacts = 0, downloads = 0;
+    uint64_t steps = 0, uploads = 0, appends = 0, compacts = 0, downloads = 0, patches = 0, subsumes = 0;
     double ms_device = 0;
 };
 

@@ -152,7 +152,7 @@ static void free_all(nb_handle h)
     cudaFree(h->d_sync);
     for (int k = 0; k < N_F64; ++k) cudaFree(*f64_fields(h->d, k));
     cudaFree(h->d.jx); cudaFree(h->d.jy); cudaFree(h->d.jz);
-    cudaFree(h->d.jm); cudaFree(h->d.fx); cudaFree(h->d.fy); cudaFree(h->d.fz);
+    cudaFree(h->d.jm); cudaFree(h->d.m0); cudaFree(h->d.computes0); cudaFree(h->d.fx); cudaFree(h->d.fy); cudaFree(h->d.fz);
     cudaFree(h->d.behavior); cudaFree(h->d.flags); cudaFree(h->d.tile_rmax);
     cudaFree(h->d.px); cudaFree(h->d.py); cudaFree(h->d.pz);
     cudaFree(h->d.render); cudaFree(h->d.render_exists);
@@ -209,6 +209,10 @@ extern "C" int nb_create(int device, int64_t capacity, int64_t pair_capacity, nb
     NB_TRY(cudaMalloc((void **)&h->d.jy, fb));
     NB_TRY(cudaMalloc((void **)&h->d.jz, fb));
     NB_TRY(cudaMalloc((void **)&h->d.jm, fb));
+    NB_TRY(cudaMalloc((void **)&h->d.m0, fb));
+    NB_TRY(cudaMemsetAsync(h->d.m0, 0, fb, h->st));
+    NB_TRY(cudaMalloc((void **)&h->d.computes0, (size_t)h->cap_pad));
+    NB_TRY(cudaMemsetAsync(h->d.computes0, 0, (size_t)h->cap_pad, h->st));
     NB_TRY(cudaMalloc((void **)&h->d.fx, fb));
     NB_TRY(cudaMalloc((void **)&h->d.fy, fb));
     NB_TRY(cudaMalloc((void **)&h->d.fz, fb));
@@ -442,7 +446,9 @@ static int finish_step(nb_handle h, nb_step_result *out)
         const Counters &c = *h->h_ctr;
         nb_step_result r{};
         r.n_bodies = h->n;
-        r.n_pairs = (h->last_opts & NB_STEP_COLLISIONS) ? c.total_pairs : 0;
+        // the event list holds collisions and subsumes; n_pairs counts the collisions
+        r.n_pairs = (h->last_opts & NB_STEP_COLLISIONS) ? c.total_pairs - (long long)c.n_sub_events : 0;
+        r.n_subsumed = (int64_t)c.n_subsumed;
         r.n_host_events = (int64_t)std::min<unsigned long long>(c.n_hev, (unsigned long long)h->hev_cap);
         r.n_resolved = (int64_t)c.n_resolved;
         r.n_culled = (int64_t)c.n_culled;
@@ -679,6 +685,9 @@ extern "C" int nb_get_pairs(nb_handle h, int32_t *i, int32_t *j, int64_t cap, in
         NB_CUDA(h, cudaMemcpy(all.data() + off, h->last_params.s.pairs_all + (long long)r * h->last_params.seg_stride,
                               c * sizeof(int2), cudaMemcpyDeviceToHost));
     }
+    // collisions only: subsume events share the device list but are reported by nb_get_host_events
+    all.erase(std::remove_if(all.begin(), all.end(), [](const int2 &a) { return (a.y & EV_SUBSUME_BIT) != 0; }),
+              all.end());
     std::sort(all.begin(), all.end(), [](const int2 &a, const int2 &b) { return a.x != b.x ? a.x < b.x : a.y < b.y; });
     *n = (int64_t)all.size();
     const int64_t m = std::min<int64_t>(cap, *n);

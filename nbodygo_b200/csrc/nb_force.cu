@@ -128,6 +128,12 @@ __global__ void __launch_bounds__(TJ) k_prep(StepParams p)
     double r = 0.0, x = 1e150, y = 1e150, z = 1e150, m = 0.0;
     if (j < p.n) {
         const unsigned fl = p.s.flags[j];
+        // calcForceFrom multiplies by the mass the body has during Compute; a subsume handled in
+        // ProcessMods changes Body.Mass before Update divides by it (body.go:120-122,241)
+        p.s.m0[j] = p.s.mass[j];
+        // ... and whether Compute runs at all is decided before ProcessMods may clear Exists (subsume) or
+        // set `fragmenting` (body.go:149-155): Update then applies the force of THIS cycle
+        p.s.computes0[j] = (fl & NB_F_EXISTS) && !(fl & NB_F_FRAGMENTING);
         const double px = p.s.x[j], py = p.s.y[j], pz = p.s.z[j];
         // a live body at a non-finite (or absurd, |coord| >= 1e150: d2 would overflow) position is
         // inert as a j-body (the reference would poison every force with NaN); as an i-body it still
@@ -181,17 +187,15 @@ __device__ __noinline__ void emit_event(const StepParams &p, long long i, long l
         else
             p.s.ctr->overflow = 1;
     } else if (bi == NB_SUBSUME || bj == NB_SUBSUME) {
-        // body.go:178-184: the larger radius subsumes, only if the centre is inside it
-        int a = -1, b = -1;
-        if (ri > rj && dist <= ri) { a = (int)i; b = (int)j; }
-        else if (rj > ri && dist <= rj) { a = (int)j; b = (int)i; }
-        if (a >= 0) {
-            const unsigned long long k = atomicAdd(&p.s.ctr->n_hev, 1ull);
-            if (k < (unsigned long long)p.hev_cap) {
-                nb_event e;
-                e.kind = NB_EV_SUBSUME; e.a = a; e.b = b; e._pad = 0; e.dist = dist; e.f1 = 0; e.f2 = 0;
-                p.s.hev[k] = e;
-            }
+        // body.go:178-184: the larger radius subsumes, only if the centre is inside it.  The event
+        // keeps its arrival position (i,j) in the one event list (K3 resolves collisions and
+        // subsumes in the reference's serial order); who subsumes whom follows from the radii.
+        if ((ri > rj && dist <= ri) || (rj > ri && dist <= rj)) {
+            const unsigned long long k = atomicAdd(&p.s.ctr->n_pairs, 1ull);
+            if (k < (unsigned long long)p.seg_cap)
+                p.s.pairs[k] = make_int2((int)i, (int)j | EV_SUBSUME_BIT);
+            else
+                p.s.ctr->overflow = 1;
         }
     }
 }

@@ -29,11 +29,11 @@ __global__ void __launch_bounds__(INT_THREADS) k_integrate(const __grid_constant
             sz += s.pz[o];
         }
         unsigned fl = s.flags[i];
-        const double m = s.mass[i];
-        const double gm = G_CONST() * m;
+        const double m = s.mass[i];          // after ProcessMods (a subsume adds the swallowed mass)
+        const double gm = G_CONST() * s.m0[i];  // calcForceFrom ran with the mass at the top of the cycle
         // Body.Compute returns early for !Exists and for fragmenting bodies (body.go:149-155): their
         // fx,fy,fz keep the value of the last cycle they computed, and Update still applies it
-        const bool computes = (fl & NB_F_EXISTS) && !(fl & NB_F_FRAGMENTING);
+        const bool computes = s.computes0[i] != 0;  // as of the top of the cycle (K0), not after ProcessMods
         const double fx = computes ? gm * sx : s.fx[i];
         const double fy = computes ? gm * sy : s.fy[i];
         const double fz = computes ? gm * sz : s.fz[i];

@@ -3,6 +3,7 @@
 // Data layout in HBM (all arrays sized to `cap_pad`, a multiple of TJ):
 //   fp64 SoA state   x y z vx vy vz mass radius rest frag_factor frag_step
 //   fp64 derived     jm   (effective j-mass: 0 for !Exists / fragmenting bodies)
+//                    m0   (mass at the top of the cycle; a subsume changes mass before Update)
 //   fp64 output      fx fy fz
 //   u8               behavior flags
 //   per-tile         tile_rmax[n_tiles]  (max radius of the live bodies of a j-tile)
@@ -30,6 +31,12 @@ constexpr int MIN_CHUNKS = 32;
 constexpr int MAX_CHUNKS = 128;
 constexpr long long CHUNK_TARGET_CTAS = 148 * 2 * 40;  // (n/512) * chunks >= this when possible
 constexpr int MAX_RANKS = 16;
+// One event list for collisions and subsumes (event.go:20-24 kinds share one queue in the reference):
+// entry = (i, j | kind bit), i = the body whose sweep raised it, j = the other body.
+constexpr int EV_SUBSUME_BIT = 1 << 30;
+constexpr int EV_INDEX_MASK = EV_SUBSUME_BIT - 1;
+// fragcalc.go: maxFrags
+constexpr double MAX_FRAGS = 2000.0;
 
 // cmd/body/body.go:19
 __host__ __device__ constexpr double G_CONST() { return 6.673e-11; }
@@ -40,6 +47,8 @@ struct Counters {
     unsigned long long n_resolved;  // doElastic applications
     unsigned long long n_culled;    // NaN-culled bodies (local shard)
     unsigned long long n_dead;      // !Exists bodies after the step (all bodies)
+    unsigned long long n_sub_events;  // subsume events in the event list (all ranks)
+    unsigned long long n_subsumed;    // bodies whose Exists was cleared by ResolveSubsume
     int overflow;                   // pair / host-event capacity exceeded
     int rounds;                     // resolve rounds
     int total_pairs;                // pairs over all ranks (set by resolve)
@@ -49,6 +58,8 @@ struct Counters {
 struct DevState {
     double *x, *y, *z, *vx, *vy, *vz, *mass, *radius, *rest, *ff, *fs;
     double *jx, *jy, *jz, *jm;  // j-stream built by K0 (sanitised positions + effective mass)
+    double *m0;                 // Body.Mass at the top of the cycle (the m_i of this cycle's force)
+    uint8_t *computes0;         // 1 if Body.Compute ran for the body this cycle (Exists && !fragmenting at the top)
     double *fx, *fy, *fz;
     uint8_t *behavior, *flags;
     double *tile_rmax;

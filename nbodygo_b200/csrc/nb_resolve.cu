@@ -4,6 +4,11 @@
 // calcElasticCollision / doElastic, cmd/body/collisioncalc.go:26-186, and
 // shouldFragment, cmd/body/fragcalc.go:24-49).
 //
+// Subsume events (Body.ResolveSubsume, cmd/body/body.go:228-244) travel in the same list with
+// their arrival position, exactly as they share the reference's one event queue, and are applied
+// here in that serial order; the flag half of initiateFragmentation (cmd/body/fragcalc.go:66-83)
+// is applied too.  The host only receives notification records (nb_get_host_events).
+//
 // Reference semantics (idealised): events are handled serially in
 // reverse arrival order; single-worker arrival order is (i asc, j asc), so the
 // resolve order is descending key = (i << 32 | j).  Two events commute unless they
@@ -98,6 +103,54 @@ __device__ CollResult calc_elastic(const DevState &s, int a, int b)
     return res;
 }
 
+__device__ void push_host_event(const StepParams &p, int kind, int a, int b, int applied, double dist, double f1,
+                                double f2)
+{
+    const unsigned long long k = atomicAdd(&p.s.ctr->n_hev, 1ull);
+    if (k < (unsigned long long)p.hev_cap) {
+        nb_event e;
+        e.kind = kind; e.a = a; e.b = b; e.applied = applied; e.dist = dist; e.f1 = f1; e.f2 = f2;
+        p.s.hev[k] = e;
+    }  // beyond the capacity the records are lost, the count is not (pair_overflow == 2)
+}
+
+// initiateFragmentation, cmd/body/fragcalc.go:66-83 — the state the next Compute sees (the
+// `fragmenting` flag); fragInfo stays with the host.  math.Min propagates NaN, fmin does not.
+__device__ void initiate_fragmentation(const DevState &s, int i, double fragFactor)
+{
+    const double ff = s.ff[i];
+    const double fragDelta = ff > 10 ? 10.0 : fragFactor - ff;
+    const double t = fragDelta * s.fs[i];
+    const double fragments = isnan(t) ? t : fmin(t, MAX_FRAGS);
+    if (fragments <= 1) {
+        s.behavior[i] = NB_FRAGMENT;
+        return;
+    }
+    s.flags[i] |= NB_F_FRAGMENTING;
+}
+
+// The subsume event raised by body i's sweep at j (body.go:178-184): the body with the larger
+// radius subsumes the other.  K1 only queues it when the centre distance is within that radius.
+// ResolveSubsume has no Exists gate: a second event for the same couple adds the 0 of SetNotExists.
+__device__ void resolve_subsume(const StepParams &p, int i, int j, bool apply)
+{
+    const DevState &s = p.s;
+    const double ri = s.radius[i], rj = s.radius[j];
+    const int a = ri > rj ? i : j, b = ri > rj ? j : i;
+    const double dx = s.x[j] - s.x[i], dy = s.y[j] - s.y[i], dz = s.z[j] - s.z[i];
+    const double dist = sqrt(dx * dx + dy * dy + dz * dz);  // unfused, as K1 computed it
+    if (apply) {
+        const double thisMass = s.mass[a], otherMass = s.mass[b];
+        s.mass[a] = thisMass + otherMass;
+        s.mass[b] = 0.0;  // SetNotExists, body.go:93-96
+        if (s.flags[b] & NB_F_EXISTS) {
+            s.flags[b] &= (uint8_t)~NB_F_EXISTS;
+            atomicAdd(&s.ctr->n_subsumed, 1ull);
+        }
+    }
+    push_host_event(p, NB_EV_SUBSUME, a, b, apply ? 1 : 0, dist, 0.0, 0.0);
+}
+
 // Body.ResolveCollision for the ready event (a,b); the caller guarantees no other
 // thread touches a or b in this round.
 __device__ void resolve_one(const StepParams &p, int a, int b)
@@ -124,15 +177,11 @@ __device__ void resolve_one(const StepParams &p, int a, int b)
         const double dvOther = fabs(s.vx[b] - nvx2) + fabs(s.vy[b] - nvy2) + fabs(s.vz[b] - nvz2);
         const double otherFactor = dvOther / fabs(vOther);
         if ((ba == NB_FRAGMENT && thisFactor > s.ff[a]) || (bb == NB_FRAGMENT && otherFactor > s.ff[b])) {
-            // doFragment is host work (fragcalc.go:54-117): hand the decision back
-            const unsigned long long k = atomicAdd(&s.ctr->n_hev, 1ull);
-            if (k < (unsigned long long)p.hev_cap) {
-                nb_event e;
-                e.kind = NB_EV_FRAGMENT; e.a = a; e.b = b; e._pad = 0; e.dist = 0; e.f1 = thisFactor; e.f2 = otherFactor;
-                s.hev[k] = e;
-            } else {
-                s.ctr->overflow = 1;
-            }
+            // doFragment, fragcalc.go:54-61: the flag half happens here, in event order; the fragInfo
+            // bookkeeping and the spawning of fragments are host work fed by this record
+            if (ba == NB_FRAGMENT && thisFactor > s.ff[a]) initiate_fragmentation(s, a, thisFactor);
+            if (bb == NB_FRAGMENT && otherFactor > s.ff[b]) initiate_fragmentation(s, b, otherFactor);
+            push_host_event(p, NB_EV_FRAGMENT, a, b, 1, 0.0, thisFactor, otherFactor);
             return;
         }
     }
@@ -170,7 +219,7 @@ __global__ void __launch_bounds__(RES_THREADS) k_resolve(const __grid_constant__
     }
     __syncthreads();
     const int total = seg_start[p.nranks];
-    if (overflow || (p.opts & (NB_STEP_NO_RESOLVE | NB_STEP_NO_INTEGRATE)) || total == 0) return;
+    if (overflow || total == 0) return;
 
     auto slot = [&](int e) -> long long {
         int r = 0;
@@ -178,15 +227,31 @@ __global__ void __launch_bounds__(RES_THREADS) k_resolve(const __grid_constant__
         return (long long)r * p.seg_stride + (e - seg_start[r]);
     };
 
+    // subsume events in the list; when nothing is resolved in this step they are only reported
+    const bool report_only = (p.opts & (NB_STEP_NO_RESOLVE | NB_STEP_NO_INTEGRATE)) != 0;
+    {
+        int subs = 0;
+        for (int e = tid; e < total; e += RES_THREADS) {
+            const int2 pr = s.pairs_all[slot(e)];
+            if (pr.y & EV_SUBSUME_BIT) {
+                ++subs;
+                if (report_only) resolve_subsume(p, pr.x, pr.y & EV_INDEX_MASK, false);
+            }
+        }
+        if (subs) atomicAdd(&s.ctr->n_sub_events, (unsigned long long)subs);
+    }
+    if (report_only) return;
+
     int rounds = 0;
     while (true) {
         // 1. publish the largest pending key per body
         for (int e = tid; e < total; e += RES_THREADS) {
             const int2 pr = s.pairs_all[slot(e)];
             if (pr.x < 0) continue;
-            const unsigned long long key = ((unsigned long long)(unsigned)pr.x << 32) | (unsigned)pr.y;
+            const int j = pr.y & EV_INDEX_MASK;
+            const unsigned long long key = ((unsigned long long)(unsigned)pr.x << 32) | (unsigned)j;
             atomicMax(&s.head[pr.x], key);
-            atomicMax(&s.head[pr.y], key);
+            atomicMax(&s.head[j], key);
         }
         __syncthreads();
         // 2. an event is ready when it heads both of its bodies
@@ -195,8 +260,9 @@ __global__ void __launch_bounds__(RES_THREADS) k_resolve(const __grid_constant__
             const long long sl = slot(e);
             int2 pr = s.pairs_all[sl];
             if (pr.x < 0) continue;
-            const unsigned long long key = ((unsigned long long)(unsigned)pr.x << 32) | (unsigned)pr.y;
-            if (__ldcg(&s.head[pr.x]) == key && __ldcg(&s.head[pr.y]) == key) {
+            const int j = pr.y & EV_INDEX_MASK;
+            const unsigned long long key = ((unsigned long long)(unsigned)pr.x << 32) | (unsigned)j;
+            if (__ldcg(&s.head[pr.x]) == key && __ldcg(&s.head[j]) == key) {
                 pr.y = -1 - pr.y;
                 s.pairs_all[sl] = pr;
             }
@@ -209,12 +275,14 @@ __global__ void __launch_bounds__(RES_THREADS) k_resolve(const __grid_constant__
             int2 pr = s.pairs_all[sl];
             if (pr.x < 0) continue;
             const bool ready = pr.y < 0;
-            const int b = ready ? -1 - pr.y : pr.y;
+            const int yk = ready ? -1 - pr.y : pr.y;  // index | kind bit
+            const int b = yk & EV_INDEX_MASK;
             s.head[pr.x] = 0ull;
             s.head[b] = 0ull;
             if (ready) {
-                resolve_one(p, pr.x, b);
-                s.pairs_all[sl] = make_int2(-1 - pr.x, b);
+                if (yk & EV_SUBSUME_BIT) resolve_subsume(p, pr.x, b, true);
+                else resolve_one(p, pr.x, b);
+                s.pairs_all[sl] = make_int2(-1 - pr.x, yk);
                 ++mine;
             }
         }

@@ -19,7 +19,7 @@ def test_header_symbols_are_exported():
     assert declared == set(capi.SYMBOLS), declared ^ set(capi.SYMBOLS)
     for sym in declared:
         assert hasattr(L, sym), sym
-    assert L.nb_abi_version() == 1
+    assert L.nb_abi_version() == 2
 
 
 def test_sm100a_sass_and_tma_present():

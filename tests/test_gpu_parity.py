@@ -69,7 +69,6 @@ def run_both(capi, b, ts, R, opts=None, steps=1):
 def test_golden_scene(capi, scene):
     b = scene_bodies(scene)
     ts, R = unhex(scene["ts"]), unhex(scene["R"])
-    has_subsume = any(k == "subsume" for st in scene["steps"] for k, *_ in st["events"])
     sim = capi.Sim(b.n)
     sim.upload(b)
     for k, step in enumerate(scene["steps"]):
@@ -86,8 +85,8 @@ def test_golden_scene(capi, scene):
         hev = sim.host_events()
         assert [(int(e["a"]), int(e["b"]), float(e["dist"])) for e in hev if e["kind"] == capi.EV_SUBSUME] == exp_sub
         got = sim.download()
-        if has_subsume:
-            break  # subsume resolution is host work (ResolveSubsume); the device does not apply it
+        # ResolveSubsume runs on the device, in event order: masses and Exists are part of the state
+        assert np.array_equal(got.mass, exp["mass"]), "mass (ResolveSubsume) must be bit-exact"
         for f in ("x", "y", "z", "vx", "vy", "vz"):
             a, r = getattr(got, f), exp[f]
             m = ~np.isnan(r)
@@ -162,7 +161,7 @@ def test_sim3_like_c1_with_sun_and_subsume(capi):
         assert np.allclose(getattr(s["state"], f), getattr(s["ref"], f), rtol=1e-12, atol=1e-4), f
 
 
-def test_subsume_events_are_handed_to_host(capi):
+def test_subsume_events_are_reported_to_host(capi):
     from oracle.oracle import EV_SUBSUME
     rng = np.random.default_rng(3)
     n = 400
@@ -180,7 +179,65 @@ def test_subsume_events_are_handed_to_host(capi):
     hev = sim.host_events()
     got = [(int(e["a"]), int(e["b"]), float(e["dist"])) for e in hev if e["kind"] == capi.EV_SUBSUME]
     assert got == ref
+    assert all(int(e["applied"]) == 1 for e in hev)
     assert np.array_equal(sim.pairs(), o.collision_pairs())
+    sim.close()
+
+
+def test_subsume_is_resolved_on_device_in_event_order(capi):
+    """ResolveSubsume (body.go:228-244) inside ProcessMods, interleaved with the elastic events of the
+    same cycle in the reference's serial order, and before Update: the swallowed body stops existing
+    (no Update), the swallower is kicked with its new mass.  Chains (A swallows B, B swallows C) make
+    the order observable.  Masses and Exists bit-exact over several cycles."""
+    rng = np.random.default_rng(11)
+    n = 600
+    b = clouds.uniform_cube(n, 60.0, 1.0, 1e12, vmax=200.0, seed=23)
+    b.radius[:] = rng.uniform(0.5, 7.0, n)
+    b.mass[:] = rng.uniform(1e11, 1e13, n)
+    b.behavior[rng.random(n) < 0.35] = SUBSUME
+    b.behavior[rng.random(n) < 0.05] = NONE
+    o = oracle_sim(b.copy())
+    sim = capi.Sim(n)
+    sim.upload(b)
+    swallowed = 0
+    for step in range(4):
+        before = o.b.exists.copy()
+        o.compute()
+        o.process_mods()
+        o.update(1e-4, 0.9)
+        res = sim.step(1e-4, 0.9)
+        g = sim.download()
+        assert np.array_equal(g.mass, o.b.mass), f"step {step}: mass"
+        assert np.array_equal(g.exists, o.b.exists), f"step {step}: Exists"
+        assert res.n_subsumed == int((before & ~o.b.exists).sum())
+        assert res.n_dead == int((~o.b.exists).sum())
+        swallowed += res.n_subsumed
+        for f in ("x", "y", "z", "vx", "vy", "vz"):
+            a, r = getattr(g, f), getattr(o.b, f)
+            assert np.allclose(a, r, rtol=1e-10, atol=1e-10 * np.max(np.abs(r))), f"step {step}: {f}"
+    assert swallowed > 20
+    # the dead bodies leave with the next compaction, exactly like BodyCollection.Cycle
+    n_new, _ = sim.compact()
+    assert n_new == int(o.b.exists.sum())
+    sim.close()
+
+
+def test_subsume_report_only_when_step_is_not_applied(capi):
+    b = BodyArrays.from_fields([0, 1, 50], [0, 0, 0], [0, 0, 0], [0, 0, 0], [0, 0, 0], [0, 0, 0],
+                               [5e10, 1e10, 1e10], [4.0, 1.0, 1.0])
+    b.behavior[:] = SUBSUME
+    sim = capi.Sim(3)
+    sim.upload(b)
+    res = sim.step(1e-3, 1.0, capi.STEP_COLLISIONS | capi.STEP_NO_INTEGRATE)
+    hev = sim.host_events()
+    assert [(int(e["a"]), int(e["b"]), int(e["applied"])) for e in hev] == [(0, 1, 0), (0, 1, 0)]
+    assert res.n_subsumed == 0 and res.n_pairs == 0
+    g = sim.download()
+    assert np.array_equal(g.mass, b.mass) and g.exists.all()
+    res = sim.step(1e-3, 1.0)
+    g = sim.download()
+    assert res.n_subsumed == 1 and list(g.mass) == [6e10, 0.0, 1e10] and list(g.exists) == [True, False, True]
+    assert [int(e["applied"]) for e in sim.host_events()] == [1, 1]
     sim.close()
 
 

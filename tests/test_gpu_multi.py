@@ -16,9 +16,29 @@ def _ndev():
         return 0
 
 
-def _rank_main(rank, world, n, steps, q_uid, q_out):
-    from nbodygo_b200 import capi
+def _cloud(n, mixed):
     b = clouds.uniform_cube(n, 70.0, 1.6, 1e12, vmax=50.0, seed=77)
+    if mixed:  # subsume chains and fragment decisions: the whole event queue is resolved on every rank
+        from nbodygo_b200.bodies import FRAGMENT, NONE, SUBSUME
+        rng = np.random.default_rng(5)
+        b.radius[:] = rng.uniform(0.4, 5.0, n)
+        b.mass[:] = rng.uniform(1e11, 1e13, n)
+        b.behavior[rng.random(n) < 0.25] = SUBSUME
+        b.behavior[rng.random(n) < 0.15] = FRAGMENT
+        b.behavior[rng.random(n) < 0.05] = NONE
+        b.frag_factor[:] = 0.05
+        b.frag_step[:] = 100.0
+    return b
+
+
+def _events(sim):
+    return sorted((int(e["kind"]), int(e["a"]), int(e["b"]), int(e["applied"]), float(e["dist"]), float(e["f1"]))
+                  for e in sim.host_events())
+
+
+def _rank_main(rank, world, n, mixed, steps, q_uid, q_out):
+    from nbodygo_b200 import capi
+    b = _cloud(n, mixed)
     sim = capi.Sim(b.n, device=rank)
     sim.upload(b)
     if rank == 0:
@@ -36,14 +56,16 @@ def _rank_main(rank, world, n, steps, q_uid, q_out):
         st = sim.download()
         out.append(dict(i0=i0, i1=i1, fx=fx[i0:i1].copy(), fy=fy[i0:i1].copy(), fz=fz[i0:i1].copy(),
                         pairs=sim.pairs(), x=st.x, vx=st.vx, vz=st.vz, flags=st.flags, rest=st.rest,
+                        mass=st.mass, behavior=st.behavior, events=_events(sim), subsumed=res.n_subsumed,
                         n_pairs=res.n_pairs, n_dead=res.n_dead, resolved=res.n_resolved))
     q_out.put((rank, out))
     sim.close()
 
 
 @pytest.mark.parametrize("peer_push", ["1", "0"], ids=["peer-push", "nccl-allgather"])
-@pytest.mark.parametrize("world,n", [(2, 5001), (2, 300), (4, 4001), (8, 9001), (8, 1000)])
-def test_sharded_step_equals_single_gpu(world, n, peer_push, monkeypatch):
+@pytest.mark.parametrize("world,n,mixed", [(2, 5001, False), (2, 300, False), (2, 2501, True), (4, 4001, False),
+                                           (8, 9001, False), (8, 1000, False), (8, 3001, True)])
+def test_sharded_step_equals_single_gpu(world, n, mixed, peer_push, monkeypatch):
     if _ndev() < world:
         pytest.skip(f"needs {world} GPUs")
     monkeypatch.setenv("NB_PEER_PUSH", peer_push)  # inherited by the spawned ranks
@@ -52,7 +74,7 @@ def test_sharded_step_equals_single_gpu(world, n, peer_push, monkeypatch):
     steps = 3
     ctx = mp.get_context("spawn")
     q_uid, q_out = ctx.Queue(), ctx.Queue()
-    procs = [ctx.Process(target=_rank_main, args=(r, world, n, steps, q_uid, q_out)) for r in range(world)]
+    procs = [ctx.Process(target=_rank_main, args=(r, world, n, mixed, steps, q_uid, q_out)) for r in range(world)]
     for p in procs:
         p.start()
     got = dict(q_out.get(timeout=300) for _ in range(world))
@@ -60,14 +82,17 @@ def test_sharded_step_equals_single_gpu(world, n, peer_push, monkeypatch):
         p.join(timeout=60)
         assert p.exitcode == 0
 
-    b = clouds.uniform_cube(n, 70.0, 1.6, 1e12, vmax=50.0, seed=77)
+    b = _cloud(n, mixed)
     sim = capi.Sim(b.n)
     sim.upload(b)
+    swallowed = 0
     for k in range(steps):
         res = sim.step(1e-3, 0.9)
         fx, fy, fz = sim.forces()
         st = sim.download()
         pairs = sim.pairs()
+        events = _events(sim)
+        swallowed += res.n_subsumed
         assert len(pairs) > 0
         for r in range(world):
             o = got[r][k]
@@ -81,6 +106,11 @@ def test_sharded_step_equals_single_gpu(world, n, peer_push, monkeypatch):
             assert np.array_equal(o["vz"].view(np.uint64), st.vz.view(np.uint64))
             assert np.array_equal(o["flags"], st.flags) and np.array_equal(o["rest"], st.rest)
             assert o["n_pairs"] == res.n_pairs and o["n_dead"] == res.n_dead and o["resolved"] == res.n_resolved
+            # ProcessMods is replicated: masses, behaviours and the event records agree on every rank
+            assert np.array_equal(o["mass"].view(np.uint64), st.mass.view(np.uint64))
+            assert np.array_equal(o["behavior"], st.behavior)
+            assert o["events"] == events and o["subsumed"] == res.n_subsumed
+    assert not mixed or swallowed > 5
     sim.close()
 
 

@@ -39,23 +39,39 @@ def _gather_var(arr: np.ndarray, world: int) -> list:
     return [o[: int(c.item())].numpy() for o, c in zip(outs, cnts)]
 
 
-def _worker(rank, world, port, n, steps, q):
+def _cloud(n, mixed):
+    b = clouds.uniform_cube(n, 40.0, 1.6, 1e12, vmax=50.0, seed=99)
+    if mixed:  # subsume chains + fragment decisions travel in the same event list
+        from nbodygo_b200.bodies import FRAGMENT, SUBSUME
+        rng = np.random.default_rng(17)
+        b.radius[:] = rng.uniform(0.4, 5.0, n)
+        b.mass[:] = rng.uniform(1e11, 1e13, n)
+        b.behavior[rng.random(n) < 0.3] = SUBSUME
+        b.behavior[rng.random(n) < 0.15] = FRAGMENT
+        b.frag_factor[:] = 0.05
+        b.frag_step[:] = 100.0
+    return b
+
+
+def _worker(rank, world, port, n, mixed, steps, q):
     from oracle.oracle import EVENT_DTYPE, EV_COLLISION, OracleSim
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    b = clouds.uniform_cube(n, 40.0, 1.6, 1e12, vmax=50.0, seed=99)
+    b = _cloud(n, mixed)
     o = OracleSim(b)
     pair_log = []
     for _ in range(steps):
         i0, i1, _, _ = capi.plan(b.n, rank, world)
         o.compute(i0, i1)                                   # K1 on the own shard
-        mine = o.collision_pairs()
-        allp = np.concatenate(_gather_var(mine.reshape(-1, 2), world))   # rank order == i order
-        pair_log.append(allp.copy())
-        ev = np.zeros(len(allp), dtype=EVENT_DTYPE)
-        ev["kind"], ev["a"], ev["b"] = EV_COLLISION, allp[:, 0], allp[:, 1]
-        o.process_mods(ev)                                  # K3 replicated on every rank
+        # the shard's event list (collisions and subsumes, arrival order) as (kind, a, b) triples —
+        # what k_push_pairs / the NCCL all-gather move between the GPUs
+        mine = np.stack([o.events["kind"], o.events["a"], o.events["b"]], axis=1).astype(np.int32)
+        alle = np.concatenate(_gather_var(mine.reshape(-1, 3), world))   # rank order == i order
+        pair_log.append(alle[alle[:, 0] == EV_COLLISION][:, 1:].copy())
+        ev = np.zeros(len(alle), dtype=EVENT_DTYPE)
+        ev["kind"], ev["a"], ev["b"] = alle[:, 0], alle[:, 1], alle[:, 2]
+        o.process_mods(ev)                                  # K3 replicated on every rank (mass, Exists too)
         o.update(1e-3, 0.9, i0, i1)                         # K4 on the own shard
         shard = (b.n + world - 1) // world
         for f in STATE:                                     # state exchange (padded equal shards)
@@ -70,28 +86,30 @@ def _worker(rank, world, port, n, steps, q):
         outs = [torch.zeros(shard, dtype=torch.uint8) for _ in range(world)]
         dist.all_gather(outs, fl)
         b.flags[:] = torch.cat(outs)[: b.n].numpy()
-    if rank == 0:
-        q.put((b.x.copy(), b.vx.copy(), b.vz.copy(), b.flags.copy(), [p.tolist() for p in pair_log]))
+    if rank == world - 1:
+        q.put((b.x.copy(), b.vx.copy(), b.vz.copy(), b.flags.copy(), b.mass.copy(), b.behavior.copy(),
+               [p.tolist() for p in pair_log]))
     dist.barrier()
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,n", [(2, 301), (3, 200)])
-def test_sharded_cycle_equals_single_rank(world, n):
+@pytest.mark.parametrize("world,n,mixed", [(2, 301, False), (3, 200, False), (2, 400, True)])
+def test_sharded_cycle_equals_single_rank(world, n, mixed):
     from oracle.oracle import OracleSim
     steps = 3
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, n, steps, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n, mixed, steps, q)) for r in range(world)]
     for p in procs:
         p.start()
-    x, vx, vz, flags, pair_log = q.get(timeout=120)
+    x, vx, vz, flags, mass, behavior, pair_log = q.get(timeout=120)
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
 
-    b = clouds.uniform_cube(n, 40.0, 1.6, 1e12, vmax=50.0, seed=99)
+    b = _cloud(n, mixed)
+    m_before = b.mass.copy()
     o = OracleSim(b)
     for k in range(steps):
         o.compute()
@@ -103,6 +121,8 @@ def test_sharded_cycle_equals_single_rank(world, n):
     assert np.array_equal(vx.view(np.uint64), b.vx.view(np.uint64))
     assert np.array_equal(vz.view(np.uint64), b.vz.view(np.uint64))
     assert np.array_equal(flags, b.flags)
+    assert np.array_equal(mass.view(np.uint64), b.mass.view(np.uint64)) and np.array_equal(behavior, b.behavior)
+    assert not mixed or ((m_before != b.mass).sum() > 10 and (~b.exists).sum() > 5)
 
 
 def test_plan_is_a_partition_and_depends_on_n_only():

@@ -213,6 +213,13 @@ int nb_plan(int64_t n, int rank, int nranks, int64_t *i0, int64_t *i1, int32_t *
  * batches on every SM and returns achieved TFLOP/s (2 flops per FMA). Used by
  * bench.py to state the roofline denominator. */
 int nb_measure_fp64_peak(int device, int iters, double *tflops, float *ms);
+/* A cycle whose parameters repeat (same body count, options, time scaling, R) is
+ * captured once into a CUDA graph and replayed with a single launch: for small
+ * collections the CPU cost of issuing the ~17 stream calls of a cycle exceeds the
+ * kernels' run time.  Single-GPU handles only; NB_GRAPH=0 in the environment turns
+ * it off.  Returns how many graphs were captured and how many cycles were replays. */
+int nb_graph_stats(nb_handle h, int64_t *captures, int64_t *replays);
+
 /* Number of kernel launches issued by this handle since creation. */
 int nb_launch_count(nb_handle h, int64_t *launches);
 

@@ -31,6 +31,7 @@ SYMBOLS = (
     "nb_compact", "nb_count", "nb_step", "nb_sync", "nb_download_state", "nb_download_render", "nb_render_buffers",
     "nb_get_forces", "nb_get_pairs", "nb_get_host_events", "nb_comm_unique_id", "nb_comm_init",
     "nb_shard_range", "nb_plan", "nb_measure_fp64_peak", "nb_launch_count",
+    "nb_graph_stats",
 )
 
 
@@ -95,6 +96,7 @@ def load(path: str | None = None):
     L.nb_plan.argtypes = [C.c_int64, C.c_int, C.c_int, _I64P, _I64P, _I32P, _I32P]
     L.nb_measure_fp64_peak.argtypes = [C.c_int, C.c_int, _DP, C.POINTER(C.c_float)]
     L.nb_launch_count.argtypes = [H, _I64P]
+    L.nb_graph_stats.argtypes = [H, _I64P, _I64P]
     if path is None:
         _LIB = L
     return L
@@ -253,6 +255,12 @@ class Sim:
         n = C.c_int64(0)
         self._chk(self.L.nb_launch_count(self.h, C.byref(n)))
         return n.value
+
+    def graph_stats(self):
+        """(graphs captured, cycles replayed from a graph)."""
+        c, r = C.c_int64(0), C.c_int64(0)
+        self._chk(self.L.nb_graph_stats(self.h, C.byref(c), C.byref(r)))
+        return c.value, r.value
 
 
 def plan(n: int, rank: int = 0, nranks: int = 1):

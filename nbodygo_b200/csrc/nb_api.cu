@@ -102,6 +102,18 @@ struct nb_sim {
     // library-owned pinned host buffers that every step fills with the Renderable snapshot
     float *h_render = nullptr;
     uint8_t *h_render_exists = nullptr;
+    // CUDA graph of one cycle (single GPU): the ~17 stream calls of a cycle cost more CPU issue time
+    // than the kernels of a small collection run (n = 1 k: ~30 us of 40), so a cycle whose
+    // parameters repeat is captured once and replayed with one cudaGraphLaunch.
+    bool graphs_enabled = true;
+    cudaGraphExec_t gexec = nullptr;
+    StepParams gkey{};        // parameters the cached graph was captured with (step_id zeroed)
+    float *gkey_render = nullptr;
+    long long g_launches = 0;  // kernel launches inside the cached graph
+    StepParams prev_key{};    // parameters of the previous step (a graph is built on the first repeat)
+    float *prev_render = nullptr;
+    bool have_prev = false;
+    unsigned long long graph_replays = 0, graph_captures = 0;
 };
 
 #define NB_CUDA(h, call)                                                                              \
@@ -146,6 +158,7 @@ static void free_all(nb_handle h)
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->st) cudaStreamSynchronize(h->st);
+    if (h->gexec) cudaGraphExecDestroy(h->gexec);
     for (void *q : h->ipc_opened) cudaIpcCloseMemHandle(q);
     if (h->comm && g_nccl.ok) g_nccl.CommDestroy(h->comm);
     cudaFree(h->d_peers);
@@ -187,6 +200,7 @@ extern "C" int nb_create(int device, int64_t capacity, int64_t pair_capacity, nb
     h->seg_cap = pair_capacity > 0 ? pair_capacity : 4 * capacity + 65536;
     h->hev_cap = h->seg_cap;
     if (const char *fr = getenv("NB_FORCE_R")) h->force_R = atoi(fr);
+    if (const char *g = getenv("NB_GRAPH")) h->graphs_enabled = atoi(g) != 0;
     auto bail = [&](const char *what, cudaError_t ce) {
         g_create_err = std::string(what) + ": " + cudaGetErrorString(ce);
         free_all(h);
@@ -497,6 +511,81 @@ static int exchange_pairs(nb_handle h, StepParams &p)
     return NB_OK;
 }
 
+// Enqueues one cycle on the handle's stream: K0 -> K1 -> [pair exchange] -> K3 -> K4 -> [state
+// exchange] -> snapshot / counter copies.  With `capturing` the same calls are recorded into a CUDA
+// graph instead (timing events become event-record nodes).  *launches = kernels issued.
+static cudaError_t record_event(nb_handle h, int k, bool capturing)
+{
+    return capturing ? cudaEventRecordWithFlags(h->ev[k], h->st, cudaEventRecordExternal)
+                     : cudaEventRecord(h->ev[k], h->st);
+}
+
+static int enqueue_cycle(nb_handle h, StepParams &p, uint32_t opts, bool capturing, long long *launches)
+{
+    long long nl = 0;
+    const long long shard = (h->n + h->nranks - 1) / h->nranks;
+    NB_CUDA(h, record_event(h, 0, capturing));
+    NB_CUDA(h, cudaMemsetAsync(h->d.ctr, 0, sizeof(Counters), h->st));
+    nl += launch_prep(p, h->st);
+    NB_CUDA(h, record_event(h, 1, capturing));
+    nl += launch_force(p, h->st, h->force_R);
+    NB_CUDA(h, record_event(h, 2, capturing));
+    if (h->nranks > 1 && (opts & NB_STEP_COLLISIONS)) {
+        if (h->peer_push) {
+            nl += launch_push_pairs(p, h->st);
+            nl += launch_peer_signal(p, PEER_SLOT_PAIRS, h->st);
+            nl += launch_peer_wait(p, PEER_SLOT_PAIRS, h->st);
+        } else {
+            int rc = exchange_pairs(h, p);
+            if (rc) return rc;
+        }
+    }
+    NB_CUDA(h, record_event(h, 3, capturing));
+    if (opts & NB_STEP_COLLISIONS) nl += launch_resolve(p, h->st);
+    NB_CUDA(h, record_event(h, 4, capturing));
+    const bool advance = !(opts & NB_STEP_NO_INTEGRATE);
+    if (h->peer_push && advance) {
+        // nobody may overwrite my replica before I have finished reading this cycle's inputs (K1, K3),
+        // and I may not overwrite a peer's before it has: publish "done reading", wait for everyone's
+        nl += launch_peer_signal(p, PEER_SLOT_DONE, h->st);
+        nl += launch_peer_wait(p, PEER_SLOT_DONE, h->st);
+    }
+    nl += launch_integrate(p, h->st);
+    NB_CUDA(h, record_event(h, 5, capturing));
+    if (h->nranks > 1) {
+        if (advance) {
+            if (h->peer_push) {
+                // K4 already stored the shard into every peer; wait until every peer's shard has landed here
+                nl += launch_peer_signal(p, PEER_SLOT_ARRIVED, h->st);
+                nl += launch_peer_wait(p, PEER_SLOT_ARRIVED, h->st);
+            } else {
+                NB_NCCL(h, g_nccl.GroupStart());
+                double *arrs[] = {h->d.x, h->d.y, h->d.z, h->d.vx, h->d.vy, h->d.vz, h->d.rest};
+                for (double *a : arrs)
+                    NB_NCCL(h, g_nccl.AllGather(a + (long long)h->rank * shard, a, (size_t)shard, NCCL_FLOAT64,
+                                                h->comm, h->st));
+                NB_NCCL(h, g_nccl.AllGather(h->d.flags + (long long)h->rank * shard, h->d.flags, (size_t)shard,
+                                            NCCL_UINT8, h->comm, h->st));
+                NB_NCCL(h, g_nccl.GroupEnd());
+            }
+        }
+        nl += launch_count_dead(p, h->st);
+    }
+    NB_CUDA(h, record_event(h, 6, capturing));
+    if (h->h_render && h->n > 0) {  // snapshot rides the same stream: in host memory when the step is synced
+        NB_CUDA(h, cudaMemcpyAsync(h->h_render, h->d.render, (size_t)h->n * 3 * sizeof(float), cudaMemcpyDeviceToHost,
+                                   h->st));
+        NB_CUDA(h, cudaMemcpyAsync(h->h_render_exists, h->d.render_exists, (size_t)h->n, cudaMemcpyDeviceToHost,
+                                   h->st));
+    }
+    NB_CUDA(h, cudaMemcpyAsync(h->h_ctr, h->d.ctr, sizeof(Counters), cudaMemcpyDeviceToHost, h->st));
+    NB_CUDA(h, cudaGetLastError());
+    *launches = nl;
+    return NB_OK;
+}
+
+static bool same_params(const StepParams &a, const StepParams &b) { return memcmp(&a, &b, sizeof(StepParams)) == 0; }
+
 extern "C" int nb_step(nb_handle h, double time_scaling, double R, uint32_t opts, nb_step_result *out)
 {
     if (!h) return NB_ERR_INVALID;
@@ -532,61 +621,51 @@ extern "C" int nb_step(nb_handle h, double time_scaling, double R, uint32_t opts
         p.s.pair_counts = h->d_pair_counts + par * MAX_RANKS;
     }
 
-    NB_CUDA(h, cudaEventRecord(h->ev[0], h->st));
-    NB_CUDA(h, cudaMemsetAsync(h->d.ctr, 0, sizeof(Counters), h->st));
-    h->launches += launch_prep(p, h->st);
-    NB_CUDA(h, cudaEventRecord(h->ev[1], h->st));
-    h->launches += launch_force(p, h->st, h->force_R);
-    NB_CUDA(h, cudaEventRecord(h->ev[2], h->st));
-    if (h->nranks > 1 && (opts & NB_STEP_COLLISIONS)) {
-        if (h->peer_push) {
-            h->launches += launch_push_pairs(p, h->st);
-            h->launches += launch_peer_signal(p, PEER_SLOT_PAIRS, h->st);
-            h->launches += launch_peer_wait(p, PEER_SLOT_PAIRS, h->st);
-        } else {
-            rc = exchange_pairs(h, p);
-            if (rc) return rc;
-        }
-    }
-    NB_CUDA(h, cudaEventRecord(h->ev[3], h->st));
-    if (opts & NB_STEP_COLLISIONS) h->launches += launch_resolve(p, h->st);
-    NB_CUDA(h, cudaEventRecord(h->ev[4], h->st));
-    const bool advance = !(opts & NB_STEP_NO_INTEGRATE);
-    if (h->peer_push && advance) {
-        // nobody may overwrite my replica before I have finished reading this cycle's inputs (K1, K3),
-        // and I may not overwrite a peer's before it has: publish "done reading", wait for everyone's
-        h->launches += launch_peer_signal(p, PEER_SLOT_DONE, h->st);
-        h->launches += launch_peer_wait(p, PEER_SLOT_DONE, h->st);
-    }
-    h->launches += launch_integrate(p, h->st);
-    NB_CUDA(h, cudaEventRecord(h->ev[5], h->st));
-    if (h->nranks > 1) {
-        if (advance) {
-            if (h->peer_push) {
-                // K4 already stored the shard into every peer; wait until every peer's shard has landed here
-                h->launches += launch_peer_signal(p, PEER_SLOT_ARRIVED, h->st);
-                h->launches += launch_peer_wait(p, PEER_SLOT_ARRIVED, h->st);
+    // ---- one cycle: replay the cached graph, or enqueue (and, on the first repeat, capture) -------
+    StepParams key = p;
+    key.step_id = 0;  // only the peer-exchange kernels read it, and those never run inside a graph
+    const bool graphable = h->graphs_enabled && h->nranks == 1 && h->n > 0;
+    if (graphable && h->gexec && same_params(key, h->gkey) && h->gkey_render == h->h_render) {
+        NB_CUDA(h, cudaGraphLaunch(h->gexec, h->st));
+        h->launches += h->g_launches;
+        h->graph_replays++;
+    } else {
+        const bool capture = graphable && h->have_prev && same_params(key, h->prev_key) && h->prev_render == h->h_render;
+        long long nl = 0;
+        if (capture) {
+            if (h->gexec) { cudaGraphExecDestroy(h->gexec); h->gexec = nullptr; }
+            cudaGraph_t graph = nullptr;
+            NB_CUDA(h, cudaStreamBeginCapture(h->st, cudaStreamCaptureModeThreadLocal));
+            rc = enqueue_cycle(h, p, opts, true, &nl);
+            const cudaError_t ce = cudaStreamEndCapture(h->st, &graph);
+            cudaError_t ci = cudaSuccess;
+            if (rc == NB_OK && ce == cudaSuccess && graph) ci = cudaGraphInstantiate(&h->gexec, graph, 0);
+            if (graph) cudaGraphDestroy(graph);
+            if (rc != NB_OK || ce != cudaSuccess || ci != cudaSuccess || !h->gexec) {
+                // never fatal: this handle goes on with plain stream launches
+                cudaGetLastError();
+                h->gexec = nullptr;
+                h->graphs_enabled = false;
+                rc = enqueue_cycle(h, p, opts, false, &nl);
+                if (rc) return rc;
+                h->launches += nl;
             } else {
-                NB_NCCL(h, g_nccl.GroupStart());
-                double *arrs[] = {h->d.x, h->d.y, h->d.z, h->d.vx, h->d.vy, h->d.vz, h->d.rest};
-                for (double *a : arrs)
-                    NB_NCCL(h, g_nccl.AllGather(a + (long long)h->rank * shard, a, (size_t)shard, NCCL_FLOAT64,
-                                                h->comm, h->st));
-                NB_NCCL(h, g_nccl.AllGather(h->d.flags + (long long)h->rank * shard, h->d.flags, (size_t)shard,
-                                            NCCL_UINT8, h->comm, h->st));
-                NB_NCCL(h, g_nccl.GroupEnd());
+                h->gkey = key;
+                h->gkey_render = h->h_render;
+                h->g_launches = nl;
+                h->graph_captures++;
+                NB_CUDA(h, cudaGraphLaunch(h->gexec, h->st));
+                h->launches += nl;
             }
+        } else {
+            rc = enqueue_cycle(h, p, opts, false, &nl);
+            if (rc) return rc;
+            h->launches += nl;
         }
-        h->launches += launch_count_dead(p, h->st);
     }
-    NB_CUDA(h, cudaEventRecord(h->ev[6], h->st));
-    if (h->h_render && h->n > 0) {  // snapshot rides the same stream: in host memory when the step is synced
-        NB_CUDA(h, cudaMemcpyAsync(h->h_render, h->d.render, (size_t)h->n * 3 * sizeof(float), cudaMemcpyDeviceToHost,
-                                   h->st));
-        NB_CUDA(h, cudaMemcpyAsync(h->h_render_exists, h->d.render_exists, (size_t)h->n, cudaMemcpyDeviceToHost,
-                                   h->st));
-    }
-    NB_CUDA(h, cudaMemcpyAsync(h->h_ctr, h->d.ctr, sizeof(Counters), cudaMemcpyDeviceToHost, h->st));
+    h->prev_key = key;
+    h->prev_render = h->h_render;
+    h->have_prev = true;
     NB_CUDA(h, cudaGetLastError());
     h->pending = true;
     h->stepped = true;
@@ -942,6 +1021,14 @@ extern "C" int nb_probe_fp64_mix(int device, int kind, int iters, double *tflops
     cudaFree(d_out);
     if (e != cudaSuccess) return NB_ERR_CUDA;
     *tflops = 2.0 * (double)blocks * 256.0 * (double)iters * 16.0 * 8.0 / (ms * 1e-3) / 1e12;
+    return NB_OK;
+}
+
+extern "C" int nb_graph_stats(nb_handle h, int64_t *captures, int64_t *replays)
+{
+    if (!h) return NB_ERR_INVALID;
+    if (captures) *captures = (int64_t)h->graph_captures;
+    if (replays) *replays = (int64_t)h->graph_replays;
     return NB_OK;
 }
 

@@ -170,6 +170,10 @@ static void free_all(nb_handle h)
     cudaFree(h->d.px); cudaFree(h->d.py); cudaFree(h->d.pz);
     cudaFree(h->d.render); cudaFree(h->d.render_exists);
     if (h->d.pairs_all != h->d.pairs) cudaFree(h->d.pairs_all);
+    cudaFree(h->d.rs_ev); cudaFree(h->d.rs_list); cudaFree(h->d.rs_state);
+    cudaFree(h->d.rs_queue); cudaFree(h->d.rs_cand); cudaFree(h->d.rs_active);
+    cudaFree(h->d.rs_lkey); cudaFree(h->d.rs_pos); cudaFree(h->d.rs_candkey);
+    cudaFree(h->d.adj_off); cudaFree(h->d.adj_cnt);
     cudaFree(h->d.pairs); cudaFree(h->d.hev); cudaFree(h->d.head); cudaFree(h->d.ctr); cudaFree(h->d.zeros);
     cudaFree(h->scratch_f64); cudaFree(h->scratch_u8); cudaFree(h->d_map); cudaFree(h->d_new_n);
     cudaFree(h->d_block_sums); cudaFree(h->d_pair_counts);
@@ -181,6 +185,28 @@ static void free_all(nb_handle h)
     for (auto &e : h->ev) if (e) cudaEventDestroy(e);
     if (h->st) cudaStreamDestroy(h->st);
     delete h;
+}
+
+// Scratch of the resolve kernel, sized for the events of all ranks.
+static cudaError_t alloc_resolve_scratch(nb_handle h, int nranks)
+{
+    cudaFree(h->d.rs_ev); cudaFree(h->d.rs_list); cudaFree(h->d.rs_state);
+    cudaFree(h->d.rs_queue); cudaFree(h->d.rs_cand); cudaFree(h->d.rs_active);
+    cudaFree(h->d.rs_lkey); cudaFree(h->d.rs_pos); cudaFree(h->d.rs_candkey);
+    h->d.rs_lkey = h->d.rs_candkey = nullptr; h->d.rs_pos = nullptr;
+    h->d.rs_ev = nullptr; h->d.rs_list = h->d.rs_state = h->d.rs_queue = h->d.rs_cand = h->d.rs_active = nullptr;
+    const size_t E = (size_t)h->seg_cap * (size_t)nranks;
+    cudaError_t e;
+    if ((e = cudaMalloc((void **)&h->d.rs_ev, E * sizeof(int2))) != cudaSuccess) return e;
+    if ((e = cudaMalloc((void **)&h->d.rs_list, 2 * E * sizeof(int))) != cudaSuccess) return e;
+    if ((e = cudaMalloc((void **)&h->d.rs_state, E * sizeof(int))) != cudaSuccess) return e;
+    if ((e = cudaMalloc((void **)&h->d.rs_queue, E * sizeof(int))) != cudaSuccess) return e;
+    if ((e = cudaMalloc((void **)&h->d.rs_cand, 2 * E * sizeof(int))) != cudaSuccess) return e;
+    if ((e = cudaMalloc((void **)&h->d.rs_active, 2 * E * sizeof(int))) != cudaSuccess) return e;
+    if ((e = cudaMalloc((void **)&h->d.rs_lkey, 2 * E * sizeof(unsigned long long))) != cudaSuccess) return e;
+    if ((e = cudaMalloc((void **)&h->d.rs_pos, E * sizeof(int2))) != cudaSuccess) return e;
+    if ((e = cudaMalloc((void **)&h->d.rs_candkey, 2 * E * sizeof(unsigned long long))) != cudaSuccess) return e;
+    return cudaSuccess;
 }
 
 extern "C" int nb_create(int device, int64_t capacity, int64_t pair_capacity, nb_handle *out)
@@ -246,6 +272,11 @@ extern "C" int nb_create(int device, int64_t capacity, int64_t pair_capacity, nb
     NB_TRY(cudaMalloc((void **)&h->d.hev, (size_t)h->hev_cap * sizeof(nb_event)));
     NB_TRY(cudaMalloc((void **)&h->d.head, (size_t)h->cap_pad * sizeof(unsigned long long)));
     NB_TRY(cudaMemsetAsync(h->d.head, 0, (size_t)h->cap_pad * sizeof(unsigned long long), h->st));
+    NB_TRY(cudaMalloc((void **)&h->d.adj_off, (size_t)h->cap_pad * sizeof(int)));
+    NB_TRY(cudaMalloc((void **)&h->d.adj_cnt, (size_t)h->cap_pad * sizeof(int)));
+    NB_TRY(cudaMemsetAsync(h->d.adj_off, 0, (size_t)h->cap_pad * sizeof(int), h->st));
+    NB_TRY(cudaMemsetAsync(h->d.adj_cnt, 0, (size_t)h->cap_pad * sizeof(int), h->st));
+    NB_TRY(alloc_resolve_scratch(h, 1));
     NB_TRY(cudaMalloc((void **)&h->d.zeros, 1024 * sizeof(unsigned)));
     NB_TRY(cudaMemsetAsync(h->d.zeros, 0, 1024 * sizeof(unsigned), h->st));
     NB_TRY(cudaMalloc((void **)&h->d.ctr, sizeof(Counters)));
@@ -924,6 +955,7 @@ extern "C" int nb_comm_init(nb_handle h, int rank, int nranks, const void *id128
     h->nranks = nranks;
     // gathered pair list: one segment per rank
     if (nranks > 1) {
+        NB_CUDA(h, alloc_resolve_scratch(h, nranks));
         const char *e = getenv("NB_PEER_PUSH");
         if (!e || atoi(e) != 0) {
             int rc = setup_peer_push(h);

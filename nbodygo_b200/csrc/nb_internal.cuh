@@ -70,7 +70,18 @@ struct DevState {
     int2 *pairs_all;           // [nranks][seg_stride] after the exchange (== pairs on one GPU)
     unsigned long long *pair_counts;  // [nranks] after the exchange
     nb_event *hev;
-    unsigned long long *head;  // [cap_pad] resolve scheduling keys
+    unsigned long long *head;  // [cap_pad] resolve scheduling: largest pending event key per body (0 between steps)
+    int *adj_off, *adj_cnt;    // [cap_pad] resolve scheduling: the body's slice of rs_list (0 between steps)
+    // resolve scratch, capacity = events of all ranks (seg_cap * nranks)
+    int2 *rs_ev;               // [E] the event list, contiguous
+    int *rs_list;              // [2E] event indices grouped by body (unsorted CSR)
+    unsigned long long *rs_lkey;  // [2E] their keys; 0 once the event is resolved
+    int2 *rs_pos;              // [E] where the event sits in its two bodies' slices
+    unsigned long long *rs_candkey;  // [2E] keys of the new-head candidates of a round
+    int *rs_state;             // [E] 0 pending, 1 queued, 2 done
+    int *rs_queue;             // [E] ready events in wavefront order
+    int *rs_cand;              // [2E] new-head candidates of a round
+    int *rs_active;            // [2E] bodies that have events this step
     Counters *ctr;
     unsigned *zeros;           // 1024 zeros (opaque low words for the rsqrt seeds in K1)
 };

@@ -208,7 +208,8 @@ def run_ours(args):
         dist.broadcast_object_list(uid, src=0)
         sim.comm_init(rank, world, uid[0])
     ts, R = args.time_scaling, 1.0
-    opts = capi.STEP_DEFAULT
+    # the roofline of K1 needs the CUDA events around it (nb_step_result.ms_force)
+    opts = capi.STEP_DEFAULT | capi.STEP_PHASE_TIMINGS
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
 
     # fp64 roofline denominator measured on this device (MEASURED_PEAKS.json has no fp64 entry)

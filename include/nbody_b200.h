@@ -61,6 +61,9 @@ extern "C" {
 #define NB_STEP_NO_RESOLVE 0x02u   /* leave elastic events unresolved (host does)   */
 #define NB_STEP_NO_INTEGRATE 0x04u /* forces + events only; state is not advanced   */
 #define NB_STEP_ASYNC 0x08u        /* enqueue only; nb_sync() collects the result   */
+#define NB_STEP_PHASE_TIMINGS 0x10u /* CUDA events between the kernels: ms_prep ... ms_integrate
+                                       (every event is a node between two kernels and costs
+                                       2-3 us of a small cycle; without it only ms_total)   */
 #define NB_STEP_DEFAULT (NB_STEP_COLLISIONS)
 
 typedef struct nb_sim *nb_handle;
@@ -76,7 +79,8 @@ typedef struct {
     int64_t n_subsumed;     /* bodies swallowed by ResolveSubsume in this step      */
     int32_t resolve_rounds; /* dependency rounds the resolve kernel needed          */
     int32_t pair_overflow;  /* 1: pair/event capacity exceeded, state NOT advanced  */
-    /* device timings of the last step, milliseconds (CUDA events) */
+    /* device timings of the last step, milliseconds (CUDA events); the per-phase
+     * values are 0 unless the step ran with NB_STEP_PHASE_TIMINGS */
     float ms_total, ms_prep, ms_force, ms_exchange, ms_resolve, ms_integrate;
 } nb_step_result;
 

@@ -21,6 +21,7 @@ STEP_COLLISIONS = 0x01
 STEP_NO_RESOLVE = 0x02
 STEP_NO_INTEGRATE = 0x04
 STEP_ASYNC = 0x08
+STEP_PHASE_TIMINGS = 0x10   # ms_prep .. ms_integrate (costs a few us of a small cycle)
 STEP_DEFAULT = STEP_COLLISIONS
 
 EV_COLLISION, EV_SUBSUME, EV_FRAGMENT = 0, 1, 2

@@ -502,13 +502,15 @@ static int finish_step(nb_handle h, nb_step_result *out)
         r.pair_overflow = c.overflow ? 1 : (c.n_hev > (unsigned long long)h->hev_cap ? 2 : 0);
         float ms = 0;
         cudaEventElapsedTime(&ms, h->ev[0], h->ev[6]); r.ms_total = ms;
-        cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]); r.ms_prep = ms;
-        cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]); r.ms_force = ms;
-        cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]); r.ms_exchange = ms;
-        cudaEventElapsedTime(&ms, h->ev[3], h->ev[4]); r.ms_resolve = ms;
-        cudaEventElapsedTime(&ms, h->ev[4], h->ev[5]); r.ms_integrate = ms;
-        float ms2 = 0;
-        cudaEventElapsedTime(&ms2, h->ev[5], h->ev[6]); r.ms_exchange += ms2;
+        if (h->last_opts & NB_STEP_PHASE_TIMINGS) {
+            cudaEventElapsedTime(&ms, h->ev[0], h->ev[1]); r.ms_prep = ms;
+            cudaEventElapsedTime(&ms, h->ev[1], h->ev[2]); r.ms_force = ms;
+            cudaEventElapsedTime(&ms, h->ev[2], h->ev[3]); r.ms_exchange = ms;
+            cudaEventElapsedTime(&ms, h->ev[3], h->ev[4]); r.ms_resolve = ms;
+            cudaEventElapsedTime(&ms, h->ev[4], h->ev[5]); r.ms_integrate = ms;
+            float ms2 = 0;
+            cudaEventElapsedTime(&ms2, h->ev[5], h->ev[6]); r.ms_exchange += ms2;
+        }
         h->last = r;
         h->pending = false;
     }
@@ -555,12 +557,14 @@ static int enqueue_cycle(nb_handle h, StepParams &p, uint32_t opts, bool capturi
 {
     long long nl = 0;
     const long long shard = (h->n + h->nranks - 1) / h->nranks;
+    const bool phases = (opts & NB_STEP_PHASE_TIMINGS) != 0;
     NB_CUDA(h, record_event(h, 0, capturing));
-    NB_CUDA(h, cudaMemsetAsync(h->d.ctr, 0, sizeof(Counters), h->st));
+    // K0 resets the step counters itself (one node less); an empty collection launches no K0
+    if (p.n_tiles <= 0) NB_CUDA(h, cudaMemsetAsync(h->d.ctr, 0, sizeof(Counters), h->st));
     nl += launch_prep(p, h->st);
-    NB_CUDA(h, record_event(h, 1, capturing));
+    if (phases) NB_CUDA(h, record_event(h, 1, capturing));
     nl += launch_force(p, h->st, h->force_R);
-    NB_CUDA(h, record_event(h, 2, capturing));
+    if (phases) NB_CUDA(h, record_event(h, 2, capturing));
     if (h->nranks > 1 && (opts & NB_STEP_COLLISIONS)) {
         if (h->peer_push) {
             nl += launch_push_pairs(p, h->st);
@@ -571,9 +575,9 @@ static int enqueue_cycle(nb_handle h, StepParams &p, uint32_t opts, bool capturi
             if (rc) return rc;
         }
     }
-    NB_CUDA(h, record_event(h, 3, capturing));
+    if (phases) NB_CUDA(h, record_event(h, 3, capturing));
     if (opts & NB_STEP_COLLISIONS) nl += launch_resolve(p, h->st);
-    NB_CUDA(h, record_event(h, 4, capturing));
+    if (phases) NB_CUDA(h, record_event(h, 4, capturing));
     const bool advance = !(opts & NB_STEP_NO_INTEGRATE);
     if (h->peer_push && advance) {
         // nobody may overwrite my replica before I have finished reading this cycle's inputs (K1, K3),
@@ -582,7 +586,7 @@ static int enqueue_cycle(nb_handle h, StepParams &p, uint32_t opts, bool capturi
         nl += launch_peer_wait(p, PEER_SLOT_DONE, h->st);
     }
     nl += launch_integrate(p, h->st);
-    NB_CUDA(h, record_event(h, 5, capturing));
+    if (phases) NB_CUDA(h, record_event(h, 5, capturing));
     if (h->nranks > 1) {
         if (advance) {
             if (h->peer_push) {

@@ -125,6 +125,9 @@ template <int TJ>
 __global__ void __launch_bounds__(TJ) k_prep(StepParams p)
 {
     const long long j = (long long)blockIdx.x * TJ + threadIdx.x;
+    // the step counters start from zero (nothing else runs on the stream while K0 does)
+    if (blockIdx.x == 0 && threadIdx.x < sizeof(Counters) / sizeof(unsigned))
+        reinterpret_cast<unsigned *>(p.s.ctr)[threadIdx.x] = 0u;
     double r = 0.0, x = 1e150, y = 1e150, z = 1e150, m = 0.0;
     if (j < p.n) {
         const unsigned fl = p.s.flags[j];
@@ -373,7 +376,10 @@ __global__ void __launch_bounds__(NT, MINB) k_force(const __grid_constant__ Step
         for (int r = 0; r < R; ++r) {
             if (lo[r] < thr[r]) {
                 double cx = 0.0, cy = 0.0, cz = 0.0;
-#pragma unroll 1
+                // small collections run about one warp per SM sub-partition, so the redo is bound by the
+                // latency of its dependent chain: unroll it where registers allow (dense clusters redo
+                // most of their tiles: Sim3 geometry, 1001 bodies)
+#pragma unroll(R == 1 ? 4 : (R == 2 ? 2 : 1))
                 for (int jj = 0; jj < TJ; jj += 2) {
                     double dx[2], dy[2], dz[2], d2[2];
 #pragma unroll

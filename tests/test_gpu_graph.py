@@ -25,7 +25,7 @@ def _run(monkeypatch, graph, steps=8):
     sim.upload(_cloud())
     out = []
     for _ in range(steps):
-        r = sim.step(1e-4, 0.9)
+        r = sim.step(1e-4, 0.9, capi.STEP_DEFAULT | capi.STEP_PHASE_TIMINGS)
         st = sim.download()
         out.append((r.n_pairs, r.n_resolved, r.n_subsumed, r.n_dead, r.n_host_events, sim.pairs().copy(),
                     st.x.copy(), st.vx.copy(), st.mass.copy(), st.flags.copy(), r.ms_total, r.ms_force))

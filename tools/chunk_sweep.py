@@ -37,8 +37,8 @@ def main():
                     os.environ.pop("NB_CHUNKS", None)
                 else:
                     os.environ["NB_CHUNKS"] = ch   # read by every nb_step
-                sim.step(1e-9, 1.0, capi.STEP_COLLISIONS | capi.STEP_NO_INTEGRATE)
-                rs = [sim.step(1e-9, 1.0, capi.STEP_COLLISIONS | capi.STEP_NO_INTEGRATE) for _ in range(a.reps)]
+                sim.step(1e-9, 1.0, capi.STEP_COLLISIONS | capi.STEP_NO_INTEGRATE | capi.STEP_PHASE_TIMINGS)
+                rs = [sim.step(1e-9, 1.0, capi.STEP_COLLISIONS | capi.STEP_NO_INTEGRATE | capi.STEP_PHASE_TIMINGS) for _ in range(a.reps)]
                 k1 = min(r.ms_force for r in rs)
                 tot = min(r.ms_total for r in rs)
                 frac = 30.0 * n * (n - 1.0) / (k1 * 1e-3) / 1e12 / peak

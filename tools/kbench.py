@@ -30,7 +30,7 @@ def main():
         os.environ["NB_FORCE_R"] = code
         sim = capi.Sim(b.n)
         sim.upload(b)
-        opts = capi.STEP_NO_INTEGRATE | (capi.STEP_COLLISIONS if a.collisions else 0)
+        opts = capi.STEP_NO_INTEGRATE | capi.STEP_PHASE_TIMINGS | (capi.STEP_COLLISIONS if a.collisions else 0)
         sim.step(1e-9, 1.0, opts)
         ms = [sim.step(1e-9, 1.0, opts).ms_force for _ in range(a.reps)]
         fx, _, _ = sim.forces()

@@ -16,7 +16,7 @@ def run(name, b, ts, steps=400):
     acc = np.zeros(8)
     mx_rounds = 0
     for k in range(steps):
-        r = sim.step(ts, 1.0)
+        r = sim.step(ts, 1.0, capi.STEP_DEFAULT | capi.STEP_PHASE_TIMINGS)
         acc += (r.ms_prep, r.ms_force, r.ms_exchange, r.ms_resolve, r.ms_integrate, r.ms_total, r.n_pairs, r.resolve_rounds)
         mx_rounds = max(mx_rounds, r.resolve_rounds)
     acc /= steps

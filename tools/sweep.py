@@ -41,7 +41,7 @@ def main():
             dist.broadcast_object_list(uid, src=0)
             sim.comm_init(rank, world, uid[0])
         for _ in range(3):
-            r = sim.step(1e-9, 1.0)
+            r = sim.step(1e-9, 1.0, capi.STEP_DEFAULT | capi.STEP_PHASE_TIMINGS)
         steps = int(max(3, min(2000, a.budget_s / max(r.ms_total * 1e-3, 1e-5))))
         if world > 1:
             t = torch.tensor([steps], device="cuda"); dist.broadcast(t, 0); steps = int(t.item())
@@ -51,7 +51,7 @@ def main():
         import time
         t0 = time.perf_counter()
         for _ in range(steps):
-            r = sim.step(1e-9, 1.0)
+            r = sim.step(1e-9, 1.0, capi.STEP_DEFAULT | capi.STEP_PHASE_TIMINGS)
             ms += r.ms_total; ms_force += r.ms_force; pairs += r.n_pairs
         wall = time.perf_counter() - t0
         if world > 1:

@@ -178,10 +178,25 @@ int launch_prep(const StepParams &p, cudaStream_t st)
 // ---------------------------------------------------------------- K1: exact path
 __device__ __forceinline__ bool elastic_or_fragment(unsigned b) { return b == NB_ELASTIC || b == NB_FRAGMENT; }
 
-__device__ __noinline__ void emit_event(const StepParams &p, long long i, long long j, double dist, double ri,
-                                        double rj)
+// The j-side facts an exact pair needs from global memory (radius, Exists, behaviour): loaded by the
+// caller for both pairs of a group at once, so that a trip of the redo costs one memory latency, not a
+// chain of them.
+struct JFacts {
+    double r;
+    unsigned flags, behavior;
+};
+__device__ __forceinline__ JFacts load_jfacts(const StepParams &p, long long j)
 {
-    const unsigned bi = p.s.behavior[i], bj = p.s.behavior[j];
+    JFacts f;  // j < n_tiles * tj <= cap_pad: in bounds even past n
+    f.r = p.s.radius[j];
+    f.flags = p.s.flags[j];
+    f.behavior = p.s.behavior[j];
+    return f;
+}
+
+__device__ __noinline__ void emit_event(const StepParams &p, long long i, long long j, double dist, double ri,
+                                        double rj, unsigned bi, unsigned bj)
+{
     if (elastic_or_fragment(bi) && elastic_or_fragment(bj)) {
         // newCollision(b, otherBody), body.go:175-177
         const unsigned long long k = atomicAdd(&p.s.ctr->n_pairs, 1ull);
@@ -206,23 +221,33 @@ __device__ __noinline__ void emit_event(const StepParams &p, long long i, long l
 // Exact restatement of calcForceFrom / Collided for one screened pair. Returns the
 // weight w = mj / dist^3 to accumulate (0 when the pair exerts no force).
 __device__ __noinline__ double exact_pair(const StepParams &p, long long i, long long j, bool alive_i, double xi,
-                                          double yi, double zi, double ri, double xj, double yj, double zj,
-                                          double mj)
+                                          double yi, double zi, double ri, unsigned bi, double xj, double yj,
+                                          double zj, double mj, JFacts fj)
 {
     if (!alive_i || j >= p.n || j == i) return 0.0;
     const double dx = __dsub_rn(xj, xi), dy = __dsub_rn(yj, yi), dz = __dsub_rn(zj, zi);
     const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
     const double dist = __dsqrt_rn(d2);
-    const double rj = p.s.radius[j];
+    const double rj = fj.r;
     const double s = __dadd_rn(ri, rj);
     if (dist > s) {
         if (mj == 0.0) return 0.0;
         return __ddiv_rn(__ddiv_rn(mj, __dmul_rn(dist, dist)), dist);
     }
     if (dist <= s) {
-        if ((p.opts & NB_STEP_COLLISIONS) && (p.s.flags[j] & NB_F_EXISTS)) emit_event(p, i, j, dist, ri, rj);
+        if ((p.opts & NB_STEP_COLLISIONS) && (fj.flags & NB_F_EXISTS)) emit_event(p, i, j, dist, ri, rj, bi, fj.behavior);
     }
     return 0.0;
+}
+
+// Conservative integer screen: a pair whose radii sum to sr can only overlap (or be degenerate) if
+// hi(d2) < hi(sr^2 (1+2^-18)) + 2.  inf / NaN radii screen every finite pair.
+__device__ __forceinline__ unsigned screen_threshold(double sr)
+{
+    const double t2 = __dmul_rn(__dmul_rn(sr, sr), 1.0 + 1.0 / 262144.0);
+    unsigned v = (unsigned)__double2hiint(t2) + 2u;
+    if (v > 0x7FF00000u) v = 0x7FF00000u;
+    return v;
 }
 
 // ---------------------------------------------------------------- K1: fast pass over one tile
@@ -340,13 +365,7 @@ __global__ void __launch_bounds__(NT, MINB) k_force(const __grid_constant__ Step
             thr[r] = 0u;
             lo[r] = 0xFFFFFFFFu;
             tx[r] = ty[r] = tz[r] = 0.0;
-            if (alive[r]) {
-                const double sr = __dadd_rn(ri[r], rm);
-                const double t2 = __dmul_rn(__dmul_rn(sr, sr), 1.0 + 1.0 / 262144.0);
-                unsigned v = (unsigned)__double2hiint(t2) + 2u;
-                if (v > 0x7FF00000u) v = 0x7FF00000u;  // inf / NaN radii: screen every finite pair
-                thr[r] = v;
-            }
+            if (alive[r]) thr[r] = screen_threshold(__dadd_rn(ri[r], rm));
         }
 
         mbar_wait(&bar[s], (unsigned)((t / NSTAGE) & 1));
@@ -370,39 +389,70 @@ __global__ void __launch_bounds__(NT, MINB) k_force(const __grid_constant__ Step
         }
 
         // ---- commit, or (rare) redo the tile carefully for a body that saw a screened pair.
-        //      The redo follows the same j order: unscreened groups {j,j+1} with the fast formula,
-        //      screened groups through exact_pair.  Which path a body takes depends on (i, tile) only.
+        //      The redo walks the tile in blocks of 64 j-bodies: first the unscreened groups {j,j+1}
+        //      with the fast formula (branch-free; the screened ones are only noted in a bit mask), then
+        //      the screened groups through exact_pair, one per trip — lanes of a warp whose screened
+        //      pairs sit at different j's make those calls together instead of one after the other
+        //      (dense clusters: the Sim3 geometry redoes most of its tiles).  Which path a body takes,
+        //      and the order of its sums, depend on (i, tile) only.
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             if (lo[r] < thr[r]) {
                 double cx = 0.0, cy = 0.0, cz = 0.0;
-                // small collections run about one warp per SM sub-partition, so the redo is bound by the
-                // latency of its dependent chain: unroll it where registers allow (dense clusters redo
-                // most of their tiles: Sim3 geometry, 1001 bodies)
+                const unsigned bi = p.s.behavior[ibase + (long long)r * NT + tid];
+                const bool fine = !(rm <= __dmul_rn(2.0, ri[r]));  // also for inf (a NaN radius in the tile)
+#pragma unroll 1
+                for (int jb = 0; jb < TJ; jb += 64) {
+                    unsigned mask = 0u;
 #pragma unroll(R == 1 ? 4 : (R == 2 ? 2 : 1))
-                for (int jj = 0; jj < TJ; jj += 2) {
-                    double dx[2], dy[2], dz[2], d2[2];
+                    for (int q = 0; q < 32; ++q) {
+                        const int jj = jb + 2 * q;
+                        double dx[2], dy[2], dz[2], d2[2];
 #pragma unroll
-                    for (int g = 0; g < 2; ++g) {
-                        dx[g] = __dsub_rn(sx[jj + g], xi[r]);
-                        dy[g] = __dsub_rn(sy[jj + g], yi[r]);
-                        dz[g] = __dsub_rn(sz[jj + g], zi[r]);
-                        d2[g] = __fma_rn(dz[g], dz[g], __fma_rn(dy[g], dy[g], __dmul_rn(dx[g], dx[g])));
-                    }
-                    const bool screened =
-                        min((unsigned)__double2hiint(d2[0]), (unsigned)__double2hiint(d2[1])) < thr[r];
-#pragma unroll
-                    for (int g = 0; g < 2; ++g) {
-                        double w;
-                        if (screened)
-                            w = exact_pair(p, ibase + (long long)r * NT + tid, jt0 + jj + g, alive[r], xi[r], yi[r],
-                                           zi[r], ri[r], sx[jj + g], sy[jj + g], sz[jj + g], sj[jj + g]);
+                        for (int g = 0; g < 2; ++g) {
+                            dx[g] = __dsub_rn(sx[jj + g], xi[r]);
+                            dy[g] = __dsub_rn(sy[jj + g], yi[r]);
+                            dz[g] = __dsub_rn(sz[jj + g], zi[r]);
+                            d2[g] = __fma_rn(dz[g], dz[g], __fma_rn(dy[g], dy[g], __dmul_rn(dx[g], dx[g])));
+                        }
+                        // When the tile's largest radius dwarfs this body's (one big body — a sun — in the
+                        // tile) the redo screens each pair with its own radius, so that the 63 tile-mates
+                        // of the sun stay on the fast formula; the loads are warp-uniform.  Otherwise the
+                        // tile-level threshold is as tight and cheaper.
+                        bool screened;
+                        if (fine)
+                            screened = (unsigned)__double2hiint(d2[0]) <
+                                           screen_threshold(__dadd_rn(ri[r], p.s.radius[jt0 + jj])) ||
+                                       (unsigned)__double2hiint(d2[1]) <
+                                           screen_threshold(__dadd_rn(ri[r], p.s.radius[jt0 + jj + 1]));
                         else
-                            w = w_from_seed(rsqrt_seed(d2[g]), d2[g], sj[jj + g]);
-                        if (w != 0.0) {
-                            cx = __fma_rn(w, dx[g], cx);
-                            cy = __fma_rn(w, dy[g], cy);
-                            cz = __fma_rn(w, dz[g], cz);
+                            screened = min((unsigned)__double2hiint(d2[0]), (unsigned)__double2hiint(d2[1])) < thr[r];
+                        mask |= (screened ? 1u : 0u) << q;
+#pragma unroll
+                        for (int g = 0; g < 2; ++g) {
+                            // a screened group's d2 may be 0: its garbage weight is masked, not branched on
+                            const double w = screened ? 0.0 : w_from_seed(rsqrt_seed(d2[g]), d2[g], sj[jj + g]);
+                            if (w != 0.0) {
+                                cx = __fma_rn(w, dx[g], cx);
+                                cy = __fma_rn(w, dy[g], cy);
+                                cz = __fma_rn(w, dz[g], cz);
+                            }
+                        }
+                    }
+                    while (mask) {
+                        const int jj = jb + 2 * (__ffs((int)mask) - 1);
+                        mask &= mask - 1u;
+                        const JFacts fj[2] = {load_jfacts(p, jt0 + jj), load_jfacts(p, jt0 + jj + 1)};
+#pragma unroll
+                        for (int g = 0; g < 2; ++g) {
+                            const double w = exact_pair(p, ibase + (long long)r * NT + tid, jt0 + jj + g, alive[r], xi[r],
+                                                        yi[r], zi[r], ri[r], bi, sx[jj + g], sy[jj + g],
+                                                        sz[jj + g], sj[jj + g], fj[g]);
+                            if (w != 0.0) {
+                                cx = __fma_rn(w, __dsub_rn(sx[jj + g], xi[r]), cx);
+                                cy = __fma_rn(w, __dsub_rn(sy[jj + g], yi[r]), cy);
+                                cz = __fma_rn(w, __dsub_rn(sz[jj + g], zi[r]), cz);
+                            }
                         }
                     }
                 }

@@ -172,7 +172,7 @@ static void free_all(nb_handle h)
     if (h->d.pairs_all != h->d.pairs) cudaFree(h->d.pairs_all);
     cudaFree(h->d.rs_ev); cudaFree(h->d.rs_list); cudaFree(h->d.rs_state);
     cudaFree(h->d.rs_queue); cudaFree(h->d.rs_cand); cudaFree(h->d.rs_active);
-    cudaFree(h->d.rs_lkey); cudaFree(h->d.rs_pos); cudaFree(h->d.rs_candkey);
+    cudaFree(h->d.rs_lkey); cudaFree(h->d.rs_pos); cudaFree(h->d.rs_candkey); cudaFree(h->d.rs_geo);
     cudaFree(h->d.adj_off); cudaFree(h->d.adj_cnt);
     cudaFree(h->d.pairs); cudaFree(h->d.hev); cudaFree(h->d.head); cudaFree(h->d.ctr); cudaFree(h->d.zeros);
     cudaFree(h->scratch_f64); cudaFree(h->scratch_u8); cudaFree(h->d_map); cudaFree(h->d_new_n);
@@ -192,8 +192,8 @@ static cudaError_t alloc_resolve_scratch(nb_handle h, int nranks)
 {
     cudaFree(h->d.rs_ev); cudaFree(h->d.rs_list); cudaFree(h->d.rs_state);
     cudaFree(h->d.rs_queue); cudaFree(h->d.rs_cand); cudaFree(h->d.rs_active);
-    cudaFree(h->d.rs_lkey); cudaFree(h->d.rs_pos); cudaFree(h->d.rs_candkey);
-    h->d.rs_lkey = h->d.rs_candkey = nullptr; h->d.rs_pos = nullptr;
+    cudaFree(h->d.rs_lkey); cudaFree(h->d.rs_pos); cudaFree(h->d.rs_candkey); cudaFree(h->d.rs_geo);
+    h->d.rs_lkey = h->d.rs_candkey = nullptr; h->d.rs_pos = nullptr; h->d.rs_geo = nullptr;
     h->d.rs_ev = nullptr; h->d.rs_list = h->d.rs_state = h->d.rs_queue = h->d.rs_cand = h->d.rs_active = nullptr;
     const size_t E = (size_t)h->seg_cap * (size_t)nranks;
     cudaError_t e;
@@ -206,6 +206,7 @@ static cudaError_t alloc_resolve_scratch(nb_handle h, int nranks)
     if ((e = cudaMalloc((void **)&h->d.rs_lkey, 2 * E * sizeof(unsigned long long))) != cudaSuccess) return e;
     if ((e = cudaMalloc((void **)&h->d.rs_pos, E * sizeof(int2))) != cudaSuccess) return e;
     if ((e = cudaMalloc((void **)&h->d.rs_candkey, 2 * E * sizeof(unsigned long long))) != cudaSuccess) return e;
+    if ((e = cudaMalloc((void **)&h->d.rs_geo, E * sizeof(ElasticGeo))) != cudaSuccess) return e;
     return cudaSuccess;
 }
 

@@ -55,6 +55,13 @@ struct Counters {
     int peer_timeout;               // a peer flag wait ran into its time limit
 };
 
+// The part of calcElasticCollision that depends on positions and radii only (fixed during
+// ProcessMods): computed for every collision event up front, in parallel, so that it is off the
+// dependent chain of the resolve rounds.
+struct __align__(16) ElasticGeo {
+    double d, st, ct, sp, cp, r12;
+};
+
 struct DevState {
     double *x, *y, *z, *vx, *vy, *vz, *mass, *radius, *rest, *ff, *fs;
     double *jx, *jy, *jz, *jm;  // j-stream built by K0 (sanitised positions + effective mass)
@@ -82,6 +89,7 @@ struct DevState {
     int *rs_queue;             // [E] ready events in wavefront order
     int *rs_cand;              // [2E] new-head candidates of a round
     int *rs_active;            // [2E] bodies that have events this step
+    ElasticGeo *rs_geo;        // [E] geometry of the collision events
     Counters *ctr;
     unsigned *zeros;           // 1024 zeros (opaque low words for the rsqrt seeds in K1)
 };

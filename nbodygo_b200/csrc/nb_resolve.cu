@@ -37,41 +37,46 @@ struct CollResult {
     double vx1, vy1, vz1, vx2, vy2, vz2, vx_cm, vy_cm, vz_cm;
 };
 
-// calcElasticCollision, cmd/body/collisioncalc.go:42-186
-__device__ CollResult calc_elastic(const DevState &s, int a, int b)
+// calcElasticCollision, cmd/body/collisioncalc.go:42-186 — the position-only part (:79,104-113):
+// distance, polar angles of r21 and their sines / cosines, r12.  Same operations, same order.
+__device__ ElasticGeo elastic_geometry(const DevState &s, int a, int b)
+{
+    ElasticGeo g;
+    g.r12 = s.radius[a] + s.radius[b];
+    const double x21 = s.x[b] - s.x[a], y21 = s.y[b] - s.y[a], z21 = s.z[b] - s.z[a];
+    g.d = sqrt(x21 * x21 + y21 * y21 + z21 * z21);
+    const double theta2 = acos(z21 / g.d);
+    const double phi2 = (x21 == 0 && y21 == 0) ? 0.0 : atan2(y21, x21);
+    // sincos shares the argument reduction of a sin/cos pair
+    sincos(theta2, &g.st, &g.ct);
+    sincos(phi2, &g.sp, &g.cp);
+    return g;
+}
+
+// calcElasticCollision, cmd/body/collisioncalc.go:42-186 — the part that depends on the bodies'
+// current velocities and masses (both change while the queue is processed)
+__device__ CollResult calc_elastic(const DevState &s, int a, int b, const ElasticGeo &g)
 {
     CollResult res;
     res.collided = false;
     const double m1 = s.mass[a], m2 = s.mass[b];
-    const double r1 = s.radius[a], r2 = s.radius[b];
-    const double x1 = s.x[a], y1 = s.y[a], z1 = s.z[a];
-    double x2 = s.x[b], y2 = s.y[b], z2 = s.z[b];
     double vx1 = s.vx[a], vy1 = s.vy[a], vz1 = s.vz[a];
     const double vx2 = s.vx[b], vy2 = s.vy[b], vz2 = s.vz[b];
 
-    const double r12 = r1 + r2;
+    const double r12 = g.r12;
     const double m21 = m2 / m1;
-    const double x21 = x2 - x1, y21 = y2 - y1, z21 = z2 - z1;
     const double vx21 = vx2 - vx1, vy21 = vy2 - vy1, vz21 = vz2 - vz1;
 
     const double vx_cm = (m1 * vx1 + m2 * vx2) / (m1 + m2);
     const double vy_cm = (m1 * vy1 + m2 * vy2) / (m1 + m2);
     const double vz_cm = (m1 * vz1 + m2 * vz2) / (m1 + m2);
 
-    const double d = sqrt(x21 * x21 + y21 * y21 + z21 * z21);
+    const double d = g.d;
     const double v = sqrt(vx21 * vx21 + vy21 * vy21 + vz21 * vz21);
     if (v == 0) return res;
 
-    x2 = x21; y2 = y21; z2 = z21;
     vx1 = -vx21; vy1 = -vy21; vz1 = -vz21;
-
-    const double theta2 = acos(z2 / d);
-    const double phi2 = (x2 == 0 && y2 == 0) ? 0.0 : atan2(y2, x2);
-    // sincos shares the argument reduction of a sin/cos pair (three libm calls fewer on the chain
-    // that bounds a resolve round)
-    double st, ct, sp, cp;
-    sincos(theta2, &st, &ct);
-    sincos(phi2, &sp, &cp);
+    const double st = g.st, ct = g.ct, sp = g.sp, cp = g.cp;
 
     double vx1r = ct * cp * vx1 + ct * sp * vy1 - st * vz1;
     double vy1r = cp * vy1 - sp * vx1;
@@ -160,13 +165,13 @@ __device__ void resolve_subsume(const StepParams &p, int i, int j, bool apply)
 
 // Body.ResolveCollision for the ready event (a,b); the caller guarantees no other
 // thread touches a or b in this round.
-__device__ void resolve_one(const StepParams &p, int a, int b)
+__device__ void resolve_one(const StepParams &p, int a, int b, const ElasticGeo &geo)
 {
     const DevState &s = p.s;
     if (!(s.flags[a] & NB_F_EXISTS) || !(s.flags[b] & NB_F_EXISTS)) return;  // body.go:249-251
     const unsigned ba = s.behavior[a], bb = s.behavior[b];
     if (!(ba == NB_ELASTIC && ef(bb))) return;  // body.go:252-253
-    const CollResult r = calc_elastic(s, a, b);
+    const CollResult r = calc_elastic(s, a, b, geo);
     if (!r.collided) return;
     const double br = s.rest[a];
     const double nvx1 = (r.vx1 - r.vx_cm) * br + r.vx_cm;
@@ -271,6 +276,7 @@ __global__ void __launch_bounds__(RES_THREADS) k_resolve(const __grid_constant__
         s.rs_ev[e] = pr;
         s.rs_state[e] = 0;
         const int i = pr.x, j = pr.y & EV_INDEX_MASK;
+        if (!(pr.y & EV_SUBSUME_BIT)) s.rs_geo[e] = elastic_geometry(s, i, j);  // positions are fixed during ProcessMods
         if (atomicAdd(&s.adj_cnt[i], 1) == 0) s.rs_active[atomicAdd(&n_active, 1)] = i;
         if (atomicAdd(&s.adj_cnt[j], 1) == 0) s.rs_active[atomicAdd(&n_active, 1)] = j;
     }
@@ -345,7 +351,7 @@ __global__ void __launch_bounds__(RES_THREADS) k_resolve(const __grid_constant__
             const int2 pr = s.rs_ev[e];
             const int2 pos = s.rs_pos[e];
             if (pr.y & EV_SUBSUME_BIT) resolve_subsume(p, pr.x, pr.y & EV_INDEX_MASK, true);
-            else resolve_one(p, pr.x, pr.y & EV_INDEX_MASK);
+            else resolve_one(p, pr.x, pr.y & EV_INDEX_MASK, s.rs_geo[e]);
             s.rs_lkey[pos.x] = 0ull;
             s.rs_lkey[pos.y] = 0ull;
         }

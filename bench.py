@@ -258,8 +258,8 @@ def run_ours(args):
             sim.step(ts, R, opts)
             sim.download_into(**out)
             sim.render(rxyz, rex)
-            for k in names[:6]:          # next cycle starts from the returned state, like the host loop
-                pinned[k][:] = out[k]
+            for k in names[:6]:          # next cycle starts from the returned state, like the host loop:
+                pinned[k], out[k] = out[k], pinned[k]   # both pinned — swap roles instead of a host memcpy
 
         e2e_step()
         barrier()

@@ -1,7 +1,7 @@
 """Debug: fragments with identical velocities overlapping a target — where do NaNs come from?"""
 import os, sys
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from nbodygo_b200.bodies import BodyArrays, ELASTIC, F_EXISTS
 from oracle.oracle import OracleSim
 

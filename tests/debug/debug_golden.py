@@ -2,7 +2,7 @@
 import sys
 import numpy as np
 import os
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "tests")]
 from helpers import load_golden, scene_bodies, scene_step_arrays, unhex
 from nbodygo_b200 import capi

@@ -8,6 +8,7 @@
  */
 #define _GNU_SOURCE
 #include "nbody_oracle.h"
+#include "gomath.h"
 
 #include <math.h>
 #include <pthread.h>
@@ -261,6 +262,26 @@ int64_t orc_compute_slice_timed(const orc_bodies *bc, int64_t i0, int64_t i1, in
     return rc ? rc : count;
 }
 
+/* ---- transcendental backend of calcElasticCollision --------------------- */
+/* ORC_MATH_LIBM (default): glibc.  ORC_MATH_GO: the Go standard library's algorithms restated in
+ * gomath.c — what the reference itself executes on amd64.  Process-wide; set before use. */
+typedef struct {
+    double (*acos_)(double), (*asin_)(double), (*sin_)(double), (*cos_)(double), (*tan_)(double);
+    double (*atan2_)(double, double);
+} math_backend;
+static const math_backend MATH_LIBM = { acos, asin, sin, cos, tan, atan2 };
+static const math_backend MATH_GO = { go_acos, go_asin, go_sin, go_cos, go_tan, go_atan2 };
+static const math_backend *g_math = &MATH_LIBM;
+
+int orc_set_math(int which)
+{
+    if (which == ORC_MATH_LIBM) g_math = &MATH_LIBM;
+    else if (which == ORC_MATH_GO) g_math = &MATH_GO;
+    else return -1;
+    return 0;
+}
+int orc_get_math(void) { return g_math == &MATH_GO ? ORC_MATH_GO : ORC_MATH_LIBM; }
+
 /* ---- calcElasticCollision, cmd/body/collisioncalc.go:42-186 ------------ */
 typedef struct {
     int collided;
@@ -295,9 +316,10 @@ static coll_result calc_elastic(const orc_bodies *bc, int64_t a, int64_t b)
     x2 = x21; y2 = y21; z2 = z21;
     vx1 = -vx21; vy1 = -vy21; vz1 = -vz21;
 
-    double theta2 = acos(z2 / d);
-    double phi2 = (x2 == 0 && y2 == 0) ? 0 : atan2(y2, x2);
-    double st = sin(theta2), ct = cos(theta2), sp = sin(phi2), cp = cos(phi2);
+    const math_backend *M = g_math;
+    double theta2 = M->acos_(z2 / d);
+    double phi2 = (x2 == 0 && y2 == 0) ? 0 : M->atan2_(y2, x2);
+    double st = M->sin_(theta2), ct = M->cos_(theta2), sp = M->sin_(phi2), cp = M->cos_(phi2);
 
     double vx1r = ct * cp * vx1 + ct * sp * vy1 - st * vz1;
     double vy1r = cp * vy1 - sp * vx1;
@@ -305,18 +327,18 @@ static coll_result calc_elastic(const orc_bodies *bc, int64_t a, int64_t b)
     double fvz1r = vz1r / v;
     if (fvz1r > 1) fvz1r = 1;
     else if (fvz1r < -1) fvz1r = -1;
-    double thetav = acos(fvz1r);
-    double phiv = (vx1r == 0 && vy1r == 0) ? 0 : atan2(vy1r, vx1r);
+    double thetav = M->acos_(fvz1r);
+    double phiv = (vx1r == 0 && vy1r == 0) ? 0 : M->atan2_(vy1r, vx1r);
 
-    double dr = d * sin(thetav) / r12;
+    double dr = d * M->sin_(thetav) / r12;
 
     if (thetav > M_PI / 2 || fabs(dr) > 1) return res; /* :137-140 */
 
-    double alpha = asin(-dr);
+    double alpha = M->asin_(-dr);
     double beta = phiv;
-    double sbeta = sin(beta), cbeta = cos(beta);
+    double sbeta = M->sin_(beta), cbeta = M->cos_(beta);
 
-    double a_ = tan(thetav + alpha);
+    double a_ = M->tan_(thetav + alpha);
     double dvz2 = 2 * (vz1r + a_ * (cbeta * vx1r + sbeta * vy1r)) / ((1 + a_ * a_) * (1 + m21));
 
     double vz2r = dvz2;

@@ -19,9 +19,12 @@
  * FP model: Go gc on amd64 — no FMA contraction, strict left-to-right
  * evaluation, math.Sqrt == SQRTSD.  Build with -ffp-contract=off, no
  * -ffast-math (see oracle/Makefile).  The Go math library transcendentals
- * (Acos/Atan2/Sin/Cos/Asin/Tan, cmd/body/collisioncalc.go:104-160) are
- * replaced by glibc libm: results of the elastic resolve may differ from Go
- * in the last ulp and carry a tolerance in the tests.
+ * (Acos/Atan2/Sin/Cos/Asin/Tan, cmd/body/collisioncalc.go:104-160) come from
+ * one of two backends (orc_set_math): glibc libm (default; the committed
+ * golden fixtures were generated with it) or a restatement of the Go standard
+ * library's own algorithms (gomath.c — what the reference executes on amd64).
+ * The two differ in the last ulp; tests/test_gomath.py measures what that does
+ * to post-collision velocities, which is why those carry a tolerance.
  */
 #ifndef NBODY_ORACLE_H
 #define NBODY_ORACLE_H
@@ -109,6 +112,11 @@ int64_t orc_compute_slice_timed(const orc_bodies *bc, int64_t i0, int64_t i1,
  * cmd/body/fragcalc.go:24-49) are appended to out_ev (may be NULL). */
 int orc_process_mods(orc_bodies *bc, const orc_event *ev, int64_t n_ev,
                      orc_event *out_ev, int64_t out_cap, int64_t *n_out);
+
+/* Transcendental backend used by calcElasticCollision (process-wide). */
+enum { ORC_MATH_LIBM = 0, ORC_MATH_GO = 1 };
+int orc_set_math(int which); /* 0, or -1 for an unknown backend */
+int orc_get_math(void);
 
 /* calcElasticCollision (cmd/body/collisioncalc.go:42-186). out[0]=collided
  * (0/1), out[1..3]=v1', out[4..6]=v2', out[7..9]=v_cm. */

@@ -43,8 +43,8 @@ assert EVENT_DTYPE.itemsize == C.sizeof(OrcEvent)
 
 def build(force: bool = False) -> str:
     so = os.path.join(_HERE, "libnbody_oracle.so")
-    src = os.path.join(_HERE, "nbody_oracle.c")
-    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+    srcs = [os.path.join(_HERE, f) for f in ("nbody_oracle.c", "nbody_oracle.h", "gomath.c", "gomath.h")]
+    if force or not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(f) for f in srcs):
         subprocess.run(["make", "-C", _HERE, "-B" if force else "-s"], check=True,
                        stdout=subprocess.DEVNULL)
     return so
@@ -69,8 +69,29 @@ def lib():
                                  C.POINTER(C.c_float), _U8P]
         L.orc_cycle_compact.argtypes = [P, I64P]
         L.orc_cycle_compact.restype = C.c_int64
+        L.orc_set_math.argtypes = [C.c_int]
+        L.orc_get_math.argtypes = []
+        for f in ("go_sin", "go_cos", "go_tan", "go_atan", "go_asin", "go_acos"):
+            getattr(L, f).argtypes = [C.c_double]
+            getattr(L, f).restype = C.c_double
+        L.go_atan2.argtypes = [C.c_double, C.c_double]
+        L.go_atan2.restype = C.c_double
         _LIB = L
     return _LIB
+
+
+MATH_LIBM, MATH_GO = 0, 1
+
+
+def set_math(which: int) -> int:
+    """Selects the transcendental backend of calcElasticCollision (process-wide): MATH_LIBM
+    (glibc, default) or MATH_GO (the Go standard library's algorithms, oracle/gomath.c).
+    Returns the previous backend."""
+    L = lib()
+    prev = L.orc_get_math()
+    if L.orc_set_math(which) != 0:
+        raise ValueError(f"unknown math backend {which}")
+    return prev
 
 
 def _dp(a):

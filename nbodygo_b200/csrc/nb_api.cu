@@ -91,6 +91,7 @@ struct nb_sim {
     unsigned last_opts = 0;
     long long launches = 0;
     int force_R = 0;
+    bool uniform_tiles = true;  // NB_UNIFORM_TILES=0 keeps every tile on the general (per-body mass) pass
     StepParams last_params{};
     // fused peer-memory exchange (K4 pushes the shard state into every peer's replica)
     bool peer_push = false;
@@ -166,7 +167,7 @@ static void free_all(nb_handle h)
     for (int k = 0; k < N_F64; ++k) cudaFree(*f64_fields(h->d, k));
     cudaFree(h->d.jx); cudaFree(h->d.jy); cudaFree(h->d.jz);
     cudaFree(h->d.jm); cudaFree(h->d.m0); cudaFree(h->d.computes0); cudaFree(h->d.fx); cudaFree(h->d.fy); cudaFree(h->d.fz);
-    cudaFree(h->d.behavior); cudaFree(h->d.flags); cudaFree(h->d.tile_rmax);
+    cudaFree(h->d.behavior); cudaFree(h->d.flags); cudaFree(h->d.tile_rmax); cudaFree(h->d.tile_muni);
     cudaFree(h->d.px); cudaFree(h->d.py); cudaFree(h->d.pz);
     cudaFree(h->d.render); cudaFree(h->d.render_exists);
     if (h->d.pairs_all != h->d.pairs) cudaFree(h->d.pairs_all);
@@ -228,6 +229,7 @@ extern "C" int nb_create(int device, int64_t capacity, int64_t pair_capacity, nb
     h->hev_cap = h->seg_cap;
     if (const char *fr = getenv("NB_FORCE_R")) h->force_R = atoi(fr);
     if (const char *g = getenv("NB_GRAPH")) h->graphs_enabled = atoi(g) != 0;
+    if (const char *u = getenv("NB_UNIFORM_TILES")) h->uniform_tiles = atoi(u) != 0;
     auto bail = [&](const char *what, cudaError_t ce) {
         g_create_err = std::string(what) + ": " + cudaGetErrorString(ce);
         free_all(h);
@@ -265,6 +267,8 @@ extern "C" int nb_create(int device, int64_t capacity, int64_t pair_capacity, nb
     NB_TRY(cudaMemsetAsync(h->d.behavior, 0, (size_t)h->cap_pad, h->st));
     NB_TRY(cudaMemsetAsync(h->d.flags, 0, (size_t)h->cap_pad, h->st));
     NB_TRY(cudaMalloc((void **)&h->d.tile_rmax, (size_t)(h->cap_pad / TJ_SMALL) * sizeof(double)));
+    NB_TRY(cudaMalloc((void **)&h->d.tile_muni, (size_t)(h->cap_pad / TJ_SMALL) * sizeof(double)));
+    NB_TRY(cudaMemsetAsync(h->d.tile_muni, 0, (size_t)(h->cap_pad / TJ_SMALL) * sizeof(double), h->st));
     NB_TRY(cudaMalloc((void **)&h->d.render, (size_t)h->cap_pad * 3 * sizeof(float)));
     NB_TRY(cudaMalloc((void **)&h->d.render_exists, (size_t)h->cap_pad));
     NB_TRY(cudaMemsetAsync(h->d.render, 0, (size_t)h->cap_pad * 3 * sizeof(float), h->st));
@@ -642,6 +646,7 @@ extern "C" int nb_step(nb_handle h, double time_scaling, double R, uint32_t opts
     p.seg_cap = h->seg_cap;
     p.hev_cap = h->hev_cap;
     p.opts = opts;
+    p.uniform_tiles = h->uniform_tiles ? 1 : 0;
     p.ts = time_scaling;
     p.R = R;
     int rc = ensure_partials(h, (long long)p.n_chunks * p.n_pad_local);

@@ -28,6 +28,17 @@
 // costs about one more, so the loop is written to keep register reads and non-FP64
 // instructions per pair minimal.
 //
+// Uniform-mass tiles: K0 notes, per j-tile, whether every body of the tile is live with exactly the
+// same mass (the generated sims and clouds of the reference give whole clusters one mass).  For
+// such a tile the mass is the same factor in every term of the tile's sum, so the fast pass
+// accumulates sum_j d_ij^-3 (x_j - x_i) — 15 FP64 instructions per pair and no LDS of the masses —
+// and the tile's mass multiplies the tile sum once at the commit.  The choice is made per j-chunk
+// (every tile of the chunk uniform, each with its own mass) and the two passes are two
+// instantiations of the kernel launched over the same grid: a CTA whose chunk is of the other kind
+// exits at once.  (Both passes in one kernel cost the hot loops their MOV-free register pairing.)
+// A property of the bodies only, like the screen: results stay independent of launch shape and
+// rank count.
+//
 // This file is compiled with -fmad=false: every FMA below is explicit.
 #include "nb_internal.cuh"
 
@@ -116,6 +127,17 @@ __device__ __forceinline__ double w_from_seed(double y0, double d2, double mj)
     return __dmul_rn(tu, c);
 }
 
+// The same without the mass: d2^(-3/2) (6 FP64 ops), for tiles whose bodies all have one mass.
+__device__ __forceinline__ double w_from_seed_uni(double y0, double d2)
+{
+    const double u = __dmul_rn(y0, y0);
+    const double e = __fma_rn(-d2, u, 1.0);
+    const double pp = __fma_rn(1.875, e, 1.5);
+    const double c = __fma_rn(e, pp, 1.0);
+    const double s = __dmul_rn(y0, u);
+    return __dmul_rn(s, c);
+}
+
 // ---------------------------------------------------------------- K0: prep
 // Builds the j-stream (jx,jy,jz,jm) K1 sweeps: jm = Exists && !fragmenting ? mass : 0 (the
 // j-filter of body.go:162-165 folded into the mass); bodies that do not exist — and the tail of
@@ -153,17 +175,34 @@ __global__ void __launch_bounds__(TJ) k_prep(StepParams p)
     p.s.jy[j] = y;
     p.s.jz[j] = z;
     p.s.jm[j] = m;
-    // block max of r (NaN radii are ignored by fmax)
-    __shared__ double red[TJ / 32];
+    // block max of r (NaN radii are ignored by fmax); block min / max of the effective mass
+    __shared__ double red[TJ / 32], red_lo[TJ / 32], red_hi[TJ / 32];
+    // a tile is "uniform" if every one of its TJ slots holds a live body with the same positive finite
+    // mass (the tail of the last tile, dead and fragmenting bodies have m = 0 and break it)
+    const int odd = __syncthreads_or(!(m > 0.0 && m < INFINITY));
+    double mlo = m, mhi = m;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) r = fmax(r, __shfl_xor_sync(0xffffffffu, r, o));
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = r;
+    for (int o = 16; o > 0; o >>= 1) {
+        r = fmax(r, __shfl_xor_sync(0xffffffffu, r, o));
+        mlo = fmin(mlo, __shfl_xor_sync(0xffffffffu, mlo, o));
+        mhi = fmax(mhi, __shfl_xor_sync(0xffffffffu, mhi, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        red[threadIdx.x >> 5] = r;
+        red_lo[threadIdx.x >> 5] = mlo;
+        red_hi[threadIdx.x >> 5] = mhi;
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
-        double mx = red[0];
+        double mx = red[0], lo = red_lo[0], hi = red_hi[0];
 #pragma unroll
-        for (int w = 1; w < TJ / 32; ++w) mx = fmax(mx, red[w]);
+        for (int w = 1; w < TJ / 32; ++w) {
+            mx = fmax(mx, red[w]);
+            lo = fmin(lo, red_lo[w]);
+            hi = fmax(hi, red_hi[w]);
+        }
         p.s.tile_rmax[blockIdx.x] = mx;
+        p.s.tile_muni[blockIdx.x] = (p.uniform_tiles && !odd && lo == hi) ? lo : 0.0;
     }
 }
 
@@ -253,7 +292,8 @@ __device__ __forceinline__ unsigned screen_threshold(double sr)
 // ---------------------------------------------------------------- K1: fast pass over one tile
 // Two j-bodies per iteration (LDS.128), R i-bodies per thread.  SELF: the tile holds bodies of this
 // CTA; the pair (i,i) gets the seed 0 (hence w == 0 exactly) and is left out of the minimum.
-template <int R, int UNR, bool SELF, int TJ>
+// UNI: every body of the tile has the same mass; the sums are taken without it (the caller scales).
+template <int R, int UNR, bool SELF, bool UNI, int TJ>
 __device__ __forceinline__ void fast_tile(const double *sx, const double *sy, const double *sz, const double *sj,
                                           const double (&xi)[R], const double (&yi)[R], const double (&zi)[R],
                                           const unsigned (&zlo)[2 * R], const int (&self_j)[R], double (&tx)[R],
@@ -264,7 +304,8 @@ __device__ __forceinline__ void fast_tile(const double *sx, const double *sy, co
         const double2 vx = *reinterpret_cast<const double2 *>(sx + jj);
         const double2 vy = *reinterpret_cast<const double2 *>(sy + jj);
         const double2 vz = *reinterpret_cast<const double2 *>(sz + jj);
-        const double2 vm = *reinterpret_cast<const double2 *>(sj + jj);
+        double2 vm = make_double2(0.0, 0.0);
+        if (!UNI) vm = *reinterpret_cast<const double2 *>(sj + jj);
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const double dxa = __dsub_rn(vx.x, xi[r]), dxb = __dsub_rn(vx.y, xi[r]);
@@ -283,8 +324,8 @@ __device__ __forceinline__ void fast_tile(const double *sx, const double *sy, co
                 yb = __hiloint2double(sb ? 0 : __double2hiint(yb), __double2loint(yb));
             }
             lo[r] = min(lo[r], min(ha, hb));
-            const double wa = w_from_seed(ya, d2a, vm.x);
-            const double wb = w_from_seed(yb, d2b, vm.y);
+            const double wa = UNI ? w_from_seed_uni(ya, d2a) : w_from_seed(ya, d2a, vm.x);
+            const double wb = UNI ? w_from_seed_uni(yb, d2b) : w_from_seed(yb, d2b, vm.y);
             tx[r] = __fma_rn(wa, dxa, tx[r]);
             ty[r] = __fma_rn(wa, dya, ty[r]);
             tz[r] = __fma_rn(wa, dza, tz[r]);
@@ -297,12 +338,17 @@ __device__ __forceinline__ void fast_tile(const double *sx, const double *sy, co
 
 // ---------------------------------------------------------------- K1: kernel
 // UNR = unroll of the j-group loop (each group is two j-bodies).
-template <int R, int NT, int MINB, int UNR, int TJ>
+// MODE: FORCE_ALL = every chunk, per-body masses; FORCE_MIXED = the same, but only the chunks that
+// hold a non-uniform tile; FORCE_UNI = only the chunks whose tiles are all uniform, masses hoisted.
+enum { FORCE_ALL = 0, FORCE_MIXED = 1, FORCE_UNI = 2 };
+
+template <int R, int NT, int MINB, int UNR, int TJ, int MODE>
 __global__ void __launch_bounds__(NT, MINB) k_force(const __grid_constant__ StepParams p)
 {
     static_assert(TJ % 2 == 0 && R <= 16, "tile of j-pairs");
     __shared__ __align__(128) double sm[NSTAGE][4][TJ];
     __shared__ __align__(8) uint64_t bar[NSTAGE];
+    constexpr bool UNI = MODE == FORCE_UNI;
 
     const int tid = threadIdx.x;
     const long long ibase = p.i0 + (long long)blockIdx.x * (NT * R);
@@ -311,6 +357,13 @@ __global__ void __launch_bounds__(NT, MINB) k_force(const __grid_constant__ Step
     int t1 = t0 + p.tiles_per_chunk;
     if (t1 > p.n_tiles) t1 = p.n_tiles;
     const int nt = t1 - t0;
+
+    if (MODE != FORCE_ALL) {  // is this chunk mine?  (block-uniform: every thread sees the same answer)
+        int mixed = 0;
+        for (int t = tid; t < nt; t += NT) mixed |= !(p.s.tile_muni[t0 + t] > 0.0);
+        const bool chunk_uni = __syncthreads_or(mixed) == 0;
+        if (chunk_uni != UNI) return;
+    }
 
     if (tid == 0) {
 #pragma unroll
@@ -380,12 +433,12 @@ __global__ void __launch_bounds__(NT, MINB) k_force(const __grid_constant__ Step
             int self_j[R];
 #pragma unroll
             for (int r = 0; r < R; ++r) self_j[r] = (int)(ibase + (long long)r * NT + tid - jt0);
-            fast_tile<R, UNR, true, TJ>(sx, sy, sz, sj, xi, yi, zi, zlo, self_j, tx, ty, tz, lo);
+            fast_tile<R, UNR, true, UNI, TJ>(sx, sy, sz, sj, xi, yi, zi, zlo, self_j, tx, ty, tz, lo);
         } else {
             int self_j[R];
 #pragma unroll
             for (int r = 0; r < R; ++r) self_j[r] = -1;
-            fast_tile<R, UNR, false, TJ>(sx, sy, sz, sj, xi, yi, zi, zlo, self_j, tx, ty, tz, lo);
+            fast_tile<R, UNR, false, UNI, TJ>(sx, sy, sz, sj, xi, yi, zi, zlo, self_j, tx, ty, tz, lo);
         }
 
         // ---- commit, or (rare) redo the tile carefully for a body that saw a screened pair.
@@ -456,7 +509,12 @@ __global__ void __launch_bounds__(NT, MINB) k_force(const __grid_constant__ Step
                         }
                     }
                 }
-                tx[r] = cx; ty[r] = cy; tz[r] = cz;
+                tx[r] = cx; ty[r] = cy; tz[r] = cz;  // the redo always carries the masses
+            } else if (UNI) {
+                const double mu = p.s.tile_muni[t0 + t];  // the one mass of every body of this tile
+                tx[r] = __dmul_rn(mu, tx[r]);
+                ty[r] = __dmul_rn(mu, ty[r]);
+                tz[r] = __dmul_rn(mu, tz[r]);
             }
             ax[r] = __dadd_rn(ax[r], tx[r]);
             ay[r] = __dadd_rn(ay[r], ty[r]);
@@ -478,14 +536,24 @@ __global__ void __launch_bounds__(NT, MINB) k_force(const __grid_constant__ Step
     }
 }
 
-template <int R, int NT, int MINB, int UNR>
+template <int R, int NT, int MINB, int UNR, bool SPLIT = false>
 static int launch_force_t(const StepParams &p, cudaStream_t st)
 {
     const long long n_local = p.i1 - p.i0;
     const long long per = (long long)NT * R;
     dim3 grid((unsigned)((n_local + per - 1) / per), (unsigned)p.n_chunks);
-    if (p.tj == TJ_SMALL) k_force<R, NT, MINB, UNR, TJ_SMALL><<<grid, NT, 0, st>>>(p);
-    else k_force<R, NT, MINB, UNR, TJ_LARGE><<<grid, NT, 0, st>>>(p);
+    if (p.tj == TJ_SMALL) {
+        // small collections: one kernel, per-body masses (a cycle is a few launches' worth of latency)
+        k_force<R, NT, MINB, UNR, TJ_SMALL, FORCE_ALL><<<grid, NT, 0, st>>>(p);
+        return 1;
+    }
+    if (SPLIT && p.uniform_tiles) {
+        // same grid twice: each CTA runs in the instantiation that matches its j-chunk and exits in the other
+        k_force<R, NT, MINB, UNR, TJ_LARGE, FORCE_UNI><<<grid, NT, 0, st>>>(p);
+        k_force<R, NT, MINB, UNR, TJ_LARGE, FORCE_MIXED><<<grid, NT, 0, st>>>(p);
+        return 2;
+    }
+    k_force<R, NT, MINB, UNR, TJ_LARGE, FORCE_ALL><<<grid, NT, 0, st>>>(p);
     return 1;
 }
 
@@ -506,9 +574,9 @@ int launch_force(const StepParams &p, cudaStream_t st, int force_R)
     // Values above 9 (NB_FORCE_R) select alternative launch shapes for tools/kbench.py:
     // 1000*UNR + 100*MINB + 10*(NT==256) + R.  Production shapes: R in {4,2,1}, NT 128.
     switch (R) {
-        case 4: return launch_force_t<4, 128, 1, 1>(p, st);
-        case 2: return launch_force_t<2, 128, 1, 1>(p, st);
-        case 1: return launch_force_t<1, 128, 1, 2>(p, st);
+        case 4: return launch_force_t<4, 128, 1, 1, true>(p, st);
+        case 2: return launch_force_t<2, 128, 1, 1, true>(p, st);
+        case 1: return launch_force_t<1, 128, 1, 2, true>(p, st);
         case 3: return launch_force_t<3, 128, 1, 1>(p, st);
         case 2004: return launch_force_t<4, 128, 1, 2>(p, st);
         case 2002: return launch_force_t<2, 128, 1, 2>(p, st);

@@ -7,6 +7,7 @@
 //   fp64 output      fx fy fz
 //   u8               behavior flags
 //   per-tile         tile_rmax[n_tiles]  (max radius of the live bodies of a j-tile)
+//                    tile_muni[n_tiles]  (the mass every body of the tile has, or 0 if they differ)
 //   partial sums     px py pz [S][n_pad_local]  (one slot per j-chunk, summed in
 //                    ascending chunk order by the integrate kernel — the result
 //                    for body i never depends on the grid or the rank count)
@@ -70,6 +71,7 @@ struct DevState {
     double *fx, *fy, *fz;
     uint8_t *behavior, *flags;
     double *tile_rmax;
+    double *tile_muni;          // > 0: every j-body of the tile is live with exactly this mass; 0: mixed (K0)
     double *px, *py, *pz;
     float *render;
     uint8_t *render_exists;
@@ -125,6 +127,7 @@ struct StepParams {
     long long seg_stride;  // stride of the per-rank segments in pairs_all
     long long hev_cap;
     unsigned opts;
+    int uniform_tiles;   // 1: K0 marks uniform-mass tiles and K1 hoists the mass out of their pair loop
     double ts, R;
 };
 

@@ -272,6 +272,27 @@ def run_ours(args):
                "h2d_bytes_per_step": int(n * (8 * 8 + 2)), "d2h_bytes_per_step": int(n * (6 * 8 + 13)),
                "ms_per_step": 1e3 * t_e2e / args.steps, "timer": "host perf_counter around synchronous C-ABI calls"}
 
+    # ---- K1 with the uniform-mass pass disabled (N=1 only; reported beside the headline) ----
+    # C4's bodies share one mass, so 31 of its 32 j-chunks run K1's uniform-mass instantiation
+    # (DESIGN.md §3).  A collection with mixed masses runs the per-body-mass pass; its K1 time on this
+    # same cloud is measured here, outside every timed region, so that both figures are on record.
+    general = None
+    if world == 1:
+        try:
+            os.environ["NB_UNIFORM_TILES"] = "0"
+            try:
+                sim_g = capi.Sim(n, device=local)      # the knob is read at nb_create
+            finally:
+                os.environ.pop("NB_UNIFORM_TILES", None)
+            sim_g.upload(bodies)
+            o_g = capi.STEP_COLLISIONS | capi.STEP_NO_INTEGRATE | capi.STEP_PHASE_TIMINGS
+            sim_g.step(ts, R, o_g)
+            ms_g = min(sim_g.step(ts, R, o_g).ms_force for _ in range(2))
+            sim_g.close()
+            general = {"ms_per_launch": ms_g}
+        except Exception as e:   # never let the side measurement cost the bench line
+            general = {"error": str(e)}
+
     # ---- CPU baseline beside it (rank 0, N=1 only) -----------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -282,6 +303,10 @@ def run_ours(args):
     if rank == 0:
         local_pairs = interactions / world
         achieved = FLOPS_PER_INTERACTION * local_pairs / t_force / 1e12
+        if general and "ms_per_launch" in general:
+            a_g = FLOPS_PER_INTERACTION * local_pairs / (general["ms_per_launch"] * 1e-3) / 1e12
+            general.update(achieved=a_g, frac=a_g / peak_burst,
+                           note="same launch with NB_UNIFORM_TILES=0: every chunk on the per-body-mass pass")
         line = {
             "metric": "fp64 body-pair interactions/s", "value": value, "unit": "interactions/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps,
@@ -298,7 +323,10 @@ def run_ours(args):
                          "peak_sustained": peak_sust, "frac_of_sustained": achieved / peak_sust,
                          "peak_nominal": NOMINAL_FP64_TFLOPS, "frac_of_nominal": achieved / NOMINAL_FP64_TFLOPS,
                          "flops_per_interaction": FLOPS_PER_INTERACTION,
-                         "ms_per_launch": 1e3 * t_force},
+                         "ms_per_launch": 1e3 * t_force,
+                         "k1_passes": "uniform-mass instantiation on the j-chunks whose tiles each hold one mass "
+                                      "(C4: 31 of 32), per-body-mass instantiation on the rest",
+                         "general_pass": general},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
         print(json.dumps(line), flush=True)

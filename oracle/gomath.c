@@ -16,8 +16,10 @@
  * PARITY UNPINNED: there is no Go toolchain in this image, so nothing here was compared with a
  * run of the real library.  What was checked (tests/test_gomath.py): the decimal coefficients
  * against the bit patterns the Go source prints beside them; every function against glibc over
- * the argument ranges the collision path can produce (<= 1 ulp apart — a mistyped coefficient
- * would show as a systematic error orders of magnitude larger); the special cases of atan2.
+ * the argument ranges the collision path can produce (1-3 ulp apart — a mistyped coefficient
+ * would show as a systematic error orders of magnitude larger); the special cases of atan2; and
+ * bit for bit against a second restatement written separately in pure Python
+ * (tests/golden/gomath_py.py), which rules out contraction / re-association by the C compiler.
  *
  * Not restated: trigReduce (Payne-Hanek, |x| >= 2^29).  The collision path only ever passes
  * angles in [-pi, 3pi/2]; beyond 2^29 these functions return NaN so that a use outside the

@@ -82,6 +82,34 @@ def test_cephes_routines_agree_with_glibc_to_a_few_ulp(name, ref, lo, hi, max_ul
     assert 0.05 < np.mean(d > 0) < 0.6   # a different algorithm, not glibc under another name
 
 
+def test_c_restatement_is_bit_identical_to_the_python_restatement():
+    # two separately written restatements of the same published algorithm, one compiled by gcc
+    # (-ffp-contract=off), one executed by CPython: a contracted or re-associated polynomial, a
+    # transcription slip in one of them, or a different octant decision would break bit equality
+    import sys
+    sys.path.insert(0, os.path.join(HERE, "golden"))
+    import gomath_py as G
+    L = oracle.lib()
+    rng = np.random.default_rng(6)
+    special = [0.0, -0.0, 1.0, -1.0, 0.5, 0.66, 0.7, 2.414213562373095, math.pi / 4, math.pi / 2, math.pi,
+               3 * math.pi / 2, 1e-300, 1e-8, 1e-7, 123456.789, 5e8, math.inf, -math.inf, math.nan]
+    wide = np.concatenate([rng.uniform(-7, 7, 30000), rng.standard_cauchy(5000) * 100, rng.uniform(-1, 1, 5000) * 1e-6,
+                           special])
+    unit = np.concatenate([rng.uniform(-1, 1, 30000), 1 - rng.uniform(0, 1e-9, 3000), [0.0, -0.0, 1.0, -1.0, 1.5, math.nan]])
+
+    def same(a, b):
+        return (a == b and math.copysign(1, a) == math.copysign(1, b)) or (math.isnan(a) and math.isnan(b))
+
+    for name, xs in (("sin", wide), ("cos", wide), ("tan", wide), ("atan", wide), ("asin", unit), ("acos", unit)):
+        c, py = getattr(L, "go_" + name), getattr(G, name)
+        for x in xs:
+            assert same(c(float(x)), py(float(x))), (name, float(x).hex())
+    ys = np.concatenate([rng.normal(size=20000), special])
+    xs = np.concatenate([rng.normal(size=20000), special[::-1]])
+    for y, x in zip(ys, xs):
+        assert same(L.go_atan2(float(y), float(x)), G.atan2(float(y), float(x))), (float(y).hex(), float(x).hex())
+
+
 def test_asin_acos_lose_accuracy_towards_one():
     # math/asin.go: asin(x) = atan(x / sqrt(1 - x*x)) (or Pi/2 - atan(sqrt(1 - x*x) / x) above 0.7),
     # acos(x) = Pi/2 - asin(x).  The rounding of x*x is amplified by 1/sqrt(1 - x*x): a few 1e-16

@@ -1,0 +1,71 @@
+"""Build-time guard on K1's hot loops (CPU: reads the SASS of the built library with cuobjdump).
+
+The loops are written against a measured issue model (profiles/r1_summary.md); a source change
+that makes ptxas spill, re-introduce per-pair MOVs or lose the tile pipeline would cost several
+per cent of the headline without failing any numerical test — and without a GPU nobody would see
+it.  This pins the instruction budget of the production instantiations instead.
+"""
+import os
+import shutil
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+
+pytestmark = pytest.mark.skipif(shutil.which("cuobjdump") is None, reason="cuobjdump not installed")
+
+PROD = "k_forceILi4ELi128ELi1ELi1ELi256"     # R = 4, 128 threads, 256-body tiles
+
+
+@pytest.fixture(scope="module")
+def loops():
+    import sass_model
+    from nbodygo_b200 import _build
+    rows = sass_model.hot_loops(_build.build(), PROD)
+    by = {}
+    for name, addr, n, hist, n_fp64, three, cycles in rows:
+        mode = int(name.split("ELi256ELi")[1][0])          # FORCE_ALL 0, FORCE_MIXED 1, FORCE_UNI 2
+        by[(mode, bool(hist.get("SEL", 0)))] = dict(n=n, hist=hist, fp64=n_fp64, three=three, cycles=cycles)
+    return by
+
+
+def test_every_production_pass_has_its_two_fast_loops(loops):
+    assert set(loops) == {(m, s) for m in (0, 1, 2) for s in (False, True)}
+
+
+@pytest.mark.parametrize("mode,fp64,lds,max_instr,max_cycles", [
+    (0, 128, 4, 152, 293),    # per-body masses: 16 FP64 instructions per pair
+    (1, 128, 4, 152, 293),
+    (2, 120, 3, 143, 276),    # uniform-mass pass: 15 per pair, no LDS of the masses
+])
+def test_fast_loop_budget(loops, mode, fp64, lds, max_instr, max_cycles):
+    L = loops[(mode, False)]
+    h = L["hist"]
+    assert L["fp64"] == fp64                      # 8 pairs per iteration
+    assert h.get("MUFU") == 8 and h.get("LDS") == lds and h.get("VIMNMX3") == 4
+    assert h.get("IMAD", 0) <= 2                  # no per-pair MOVs (the seeds pair with live zero registers)
+    assert not any(k in h for k in ("LDL", "STL", "LDG", "CALL", "BAR", "SEL", "ISETP"))
+    assert L["n"] <= max_instr and L["cycles"] <= max_cycles, (L["n"], L["cycles"])
+
+
+def test_self_tile_loops_are_branch_free_too(loops):
+    for mode, fp64 in ((0, 128), (1, 128), (2, 120)):
+        L = loops[(mode, True)]
+        assert L["fp64"] == fp64 and L["hist"].get("BRA") == 1
+        assert not any(k in L["hist"] for k in ("LDL", "STL", "CALL", "BAR"))
+
+
+def test_production_kernels_do_not_spill():
+    import subprocess
+    from nbodygo_b200 import _build
+    out = subprocess.run(["cuobjdump", "-res-usage", _build.build()], capture_output=True, text=True, check=True).stdout
+    lines = out.splitlines()
+    seen = 0
+    for i, line in enumerate(lines):
+        if PROD in line:
+            use = lines[i + 1]
+            assert "STACK:0" in use and "LOCAL:0" in use, use
+            seen += 1
+    assert seen == 3

@@ -303,6 +303,13 @@ def run_ours(args):
     if rank == 0:
         local_pairs = interactions / world
         achieved = FLOPS_PER_INTERACTION * local_pairs / t_force / 1e12
+        k1_passes = ("uniform-mass instantiation on the j-chunks whose tiles each hold one mass, per-body-mass "
+                     "instantiation on the rest")
+        try:
+            nu, nc, _, _ = capi.uniform_chunks(bodies)
+            k1_passes += f" ({args.config}: {nu} of {nc} chunks uniform)"
+        except Exception:
+            pass
         if general and "ms_per_launch" in general:
             a_g = FLOPS_PER_INTERACTION * local_pairs / (general["ms_per_launch"] * 1e-3) / 1e12
             general.update(achieved=a_g, frac=a_g / peak_burst,
@@ -324,8 +331,7 @@ def run_ours(args):
                          "peak_nominal": NOMINAL_FP64_TFLOPS, "frac_of_nominal": achieved / NOMINAL_FP64_TFLOPS,
                          "flops_per_interaction": FLOPS_PER_INTERACTION,
                          "ms_per_launch": 1e3 * t_force,
-                         "k1_passes": "uniform-mass instantiation on the j-chunks whose tiles each hold one mass "
-                                      "(C4: 31 of 32), per-body-mass instantiation on the rest",
+                         "k1_passes": k1_passes,
                          "general_pass": general},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }

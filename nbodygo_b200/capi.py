@@ -274,6 +274,31 @@ def plan(n: int, rank: int = 0, nranks: int = 1):
     return i0.value, i1.value, nc.value, tpc.value
 
 
+def uniform_chunks(b: BodyArrays):
+    """(uniform j-chunks, j-chunks, uniform tiles, tiles) of K1 for this collection — the host-side
+    mirror of K0's `tile_muni` rule and K1's per-chunk dispatch (nb_force.cu), for reports and tests:
+    a tile is uniform if all its slots hold live, non-fragmenting bodies of one positive finite mass;
+    a chunk runs the uniform-mass pass if all its tiles are.  Collections below 16,384 bodies use
+    64-body tiles and a single per-body-mass launch (returns 0 uniform chunks for them)."""
+    from .bodies import F_EXISTS, F_FRAGMENTING
+    n = b.n
+    _, _, n_chunks, tpc = plan(n)
+    tj = 64 if n < 16384 else 256
+    n_tiles = (n + tj - 1) // tj
+    m = np.zeros(n_tiles * tj)
+    live = ((b.flags & F_EXISTS) != 0) & ((b.flags & F_FRAGMENTING) == 0)
+    m[:n] = np.where(live, b.mass, 0.0)
+    m = m.reshape(n_tiles, tj)
+    with np.errstate(invalid="ignore"):
+        ok = np.all((m > 0) & (m < np.inf), axis=1) & (m.min(axis=1) == m.max(axis=1))
+    if tj == 64:
+        return 0, n_chunks, int(ok.sum()), n_tiles
+    pad = np.ones(n_chunks * tpc, dtype=bool)
+    pad[:n_tiles] = ok
+    per_chunk = pad.reshape(n_chunks, tpc).all(axis=1)
+    return int(per_chunk.sum()), n_chunks, int(ok.sum()), n_tiles
+
+
 def comm_unique_id() -> bytes:
     L = load()
     buf = C.create_string_buffer(128)

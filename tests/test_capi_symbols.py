@@ -49,3 +49,21 @@ def test_product_package_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.replace("the oracle", "").replace("CPU oracle", "") or f == "clouds.py", f
+
+
+def test_uniform_chunk_report_mirrors_the_device_rule():
+    # host-side mirror of K0's tile rule / K1's chunk dispatch (pure arithmetic + nb_plan, no device)
+    import numpy as np
+    from nbodygo_b200 import capi, clouds
+    from nbodygo_b200.bodies import F_EXISTS
+    b = clouds.config("C4")
+    assert capi.uniform_chunks(b)[:2] == (31, 32)          # the chunk with the tail tile stays general
+    b.flags[5] &= ~np.uint8(F_EXISTS)                      # a dead body: its chunk goes general too
+    assert capi.uniform_chunks(b)[:2] == (30, 32)
+    c2 = clouds.config("C2")                               # 10 k bodies, masses U[1e24, 1e25]: single launch
+    assert capi.uniform_chunks(c2)[0] == 0
+    c3 = clouds.config("C3")
+    nu, nc, tu, nt = capi.uniform_chunks(c3)
+    assert nu == nc - 1 and tu == nt - 1                   # 100 k equal masses: all but the tail
+    c3.mass[::256] *= 1.5
+    assert capi.uniform_chunks(c3)[0] == 0 and capi.uniform_chunks(c3)[2] == 0

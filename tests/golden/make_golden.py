@@ -9,7 +9,8 @@ no FMA, strict left-to-right — the same FP model as Go gc/amd64), following
   cmd/body/collisioncalc.go:26-186
   cmd/body/body_collection.go:212-233 (reverse-arrival resolve order)
 so that the C oracle is checked against something other than itself.  The
-transcendentals come from Python's math module (glibc libm), as in the C oracle.
+transcendentals come from Python's math module (glibc libm), as in the C oracle's default backend
+(module attribute `M`; see tests/test_gomath.py for the Go-library variant).
 
 Run:  python tests/golden/make_golden.py   (rewrites golden.json deterministically)
 """
@@ -20,6 +21,11 @@ import struct
 
 G = 6.673e-11
 NONE, SUBSUME, ELASTIC, FRAGMENT = 0, 1, 2, 3
+
+# Transcendentals of calcElasticCollision.  `math` (glibc) for the committed golden.json, like the C
+# oracle's default backend; tests/test_gomath.py swaps in tests/golden/gomath_py.py (the Go standard
+# library's algorithms restated) and compares the scenes with the C oracle's Go backend bit for bit.
+M = math
 
 
 def hx(v):
@@ -103,10 +109,10 @@ def calc_elastic(b, o):
         q = z2 / d
     except ZeroDivisionError:
         q = math.nan  # Go: 0/0 = NaN, no panic for floats
-    theta2 = math.acos(q) if not math.isnan(q) else math.nan
-    phi2 = 0.0 if (x2 == 0 and y2 == 0) else math.atan2(y2, x2)
-    st, ct = (math.sin(theta2), math.cos(theta2)) if not math.isnan(theta2) else (math.nan, math.nan)
-    sp, cp = math.sin(phi2), math.cos(phi2)
+    theta2 = M.acos(q) if not math.isnan(q) else math.nan
+    phi2 = 0.0 if (x2 == 0 and y2 == 0) else M.atan2(y2, x2)
+    st, ct = (M.sin(theta2), M.cos(theta2)) if not math.isnan(theta2) else (math.nan, math.nan)
+    sp, cp = M.sin(phi2), M.cos(phi2)
     vx1r = ct * cp * vx1 + ct * sp * vy1 - st * vz1
     vy1r = cp * vy1 - sp * vx1
     vz1r = st * cp * vx1 + st * sp * vy1 + ct * vz1
@@ -115,15 +121,15 @@ def calc_elastic(b, o):
         fvz1r = 1.0
     elif fvz1r < -1:
         fvz1r = -1.0
-    thetav = math.acos(fvz1r) if not math.isnan(fvz1r) else math.nan
-    phiv = 0.0 if (vx1r == 0 and vy1r == 0) else math.atan2(vy1r, vx1r)
-    dr = d * (math.sin(thetav) if not math.isnan(thetav) else math.nan) / r12
+    thetav = M.acos(fvz1r) if not math.isnan(fvz1r) else math.nan
+    phiv = 0.0 if (vx1r == 0 and vy1r == 0) else M.atan2(vy1r, vx1r)
+    dr = d * (M.sin(thetav) if not math.isnan(thetav) else math.nan) / r12
     if thetav > math.pi / 2 or abs(dr) > 1:
         return None
-    alpha = math.asin(-dr) if not math.isnan(dr) else math.nan
+    alpha = M.asin(-dr) if not math.isnan(dr) else math.nan
     beta = phiv
-    sbeta, cbeta = (math.sin(beta), math.cos(beta)) if not math.isnan(beta) else (math.nan, math.nan)
-    a = math.tan(thetav + alpha) if not math.isnan(thetav + alpha) else math.nan
+    sbeta, cbeta = (M.sin(beta), M.cos(beta)) if not math.isnan(beta) else (math.nan, math.nan)
+    a = M.tan(thetav + alpha) if not math.isnan(thetav + alpha) else math.nan
     dvz2 = 2 * (vz1r + a * (cbeta * vx1r + sbeta * vy1r)) / ((1 + a * a) * (1 + m21))
     vz2r = dvz2
     vx2r = a * cbeta * dvz2

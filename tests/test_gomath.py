@@ -297,3 +297,44 @@ def test_libm_choice_does_not_change_a_dense_trajectory_beyond_1e12(go_math):
         assert np.max(np.abs(getattr(go.b, f) - getattr(lm.b, f))) <= 1e-12 * size
     for f in ("vx", "vy", "vz"):
         assert np.max(np.abs(getattr(go.b, f) - getattr(lm.b, f))) <= 1e-12 * 2.0e9
+
+
+def test_scenes_with_go_math_python_restatement_equals_c_oracle_bit_for_bit(go_math):
+    """The golden scenes once more, with Go's transcendentals on both sides: the pure-Python
+    restatement of the cycle (tests/golden/make_golden.py) on tests/golden/gomath_py.py against the
+    C oracle on oracle/gomath.c — forces, events, post-collision velocities, positions, culls."""
+    import sys
+    sys.path.insert(0, os.path.join(HERE, "golden"))
+    import gomath_py
+    import make_golden
+    from helpers import same_bits, scene_bodies, scene_step_arrays, unhex
+    from oracle.oracle import EV_COLLISION, EV_SUBSUME
+    kind = {"collision": EV_COLLISION, "subsume": EV_SUBSUME}
+    prev = make_golden.M
+    make_golden.M = gomath_py
+    try:
+        scenes = make_golden.scenes()
+    finally:
+        make_golden.M = prev
+    collided = 0
+    for scene in scenes:
+        b = scene_bodies(scene)
+        o = OracleSim(b)
+        ts, R = unhex(scene["ts"]), unhex(scene["R"])
+        for step in scene["steps"]:
+            exp = scene_step_arrays(step)
+            o.compute()
+            live = b.exists
+            assert same_bits(np.stack([o.fx, o.fy, o.fz], axis=1)[live], exp["forces"][live])
+            assert [(int(e["kind"]), int(e["a"]), int(e["b"])) for e in o.events] == \
+                   [(kind[k], a, b_) for k, a, b_, _ in step["events"]]
+            collided += len(o.events)
+            o.process_mods()
+            o.update(ts, R)
+            for f in ("x", "y", "z", "vx", "vy", "vz", "mass"):
+                assert same_bits(getattr(b, f), exp[f]), (scene["name"], f)
+            assert np.array_equal(b.exists, exp["exists"])
+    assert collided > 100
+    # and the Go-library scenes are not the glibc scenes: the backend switch reaches the oracle
+    glibc = {s["name"]: s for s in make_golden.scenes()}
+    assert any(s["steps"][-1]["state"] != glibc[s["name"]]["steps"][-1]["state"] for s in scenes)

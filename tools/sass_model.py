@@ -3,8 +3,8 @@
 
   python tools/sass_model.py [--kernel SUBSTRING] [--so PATH]
 
-For every loop of the selected k_force instantiations that contains more than 100 instructions and
-no call, prints: instruction count by opcode, FP64 instructions, distinct 64-bit register operands
+For every loop of the selected k_force instantiations that contains more than 40 instructions, at
+least 30 of them FP64, and no call, barrier or global / local memory access, prints: instruction count by opcode, FP64 instructions, distinct 64-bit register operands
 they read (the `.reuse` cache of the previous instruction taken into account), and the cycles per
 iteration predicted by the issue model measured on B200 (profiles/r1_summary.md):
 
@@ -50,7 +50,7 @@ def opcode(text):
     return op.split(".")[0]
 
 
-def loops(instrs, min_len=100):
+def loops(instrs, min_len=40):
     """Innermost backward-branch loops [(start index, end index)] with more than min_len instructions."""
     addr = {a: i for i, (a, _) in enumerate(instrs)}
     found = []
@@ -110,7 +110,7 @@ def hot_loops(so, kernel_filter=""):
         for a, b in loops(instrs):
             body = instrs[a:b + 1]
             hist, n_fp64, reads, three, cycles, impure = cost(body)
-            if impure or n_fp64 < 100:
+            if impure or n_fp64 < 30:
                 continue   # the redo / exact paths, not the fast pass
             rows.append((name, instrs[a][0], len(body), hist, n_fp64, three, cycles))
     return rows

@@ -43,3 +43,69 @@ def test_cuda_arm_has_no_cpu_fallback():
                         "--bodies", "1000"], capture_output=True, text=True, timeout=300)
     assert r.returncode != 0
     assert "no CUDA device" in (r.stderr + r.stdout)
+
+
+def test_cuda_arm_json_assembly_with_a_stub_device(monkeypatch, capsys):
+    """Runs bench.run_ours in-process with the device calls stubbed out (torch.cuda, capi.Sim and the
+    peak probe): no number it prints means anything, but every line of the JSON assembly executes —
+    a typo there would otherwise first show on the GPU box at round end."""
+    import importlib
+    import types
+
+    import numpy as np
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a device is present: the real arm is exercised by the driver")
+    sys.path.insert(0, ROOT)
+    bench = importlib.import_module("bench")
+    from nbodygo_b200 import capi
+
+    class StubResult:
+        ms_total, ms_force, n_pairs, resolve_rounds = 2.0, 1.5, 7, 2
+
+    class StubSim:
+        created = 0
+
+        def __init__(self, capacity, device=0, pair_capacity=0):
+            StubSim.created += 1
+            self.n, self._l = capacity, 0
+            self.uniform = os.environ.get("NB_UNIFORM_TILES", "1")
+
+        def upload(self, b): pass
+        def upload_raw(self, n, *a, **k): assert len(a) == 8 and all(len(x) == n for x in a)
+
+        def step(self, ts, R, opts=capi.STEP_DEFAULT):
+            self._l += 5
+            return StubResult()
+
+        def download_into(self, **out): assert set(out) == {"x", "y", "z", "vx", "vy", "vz"}
+        def render(self, xyz, ex): assert xyz.shape == (self.n, 3)
+        def launch_count(self): return self._l
+        def close(self): pass
+
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    monkeypatch.setattr(torch.cuda, "set_device", lambda d: None)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a: None)
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self: self)
+    real_empty = torch.empty
+    monkeypatch.setattr(torch, "empty", lambda *a, **k: real_empty(*a, **{kk: v for kk, v in k.items() if kk != "device"}))
+    monkeypatch.setattr(capi, "Sim", StubSim)
+    monkeypatch.setattr(capi, "measure_fp64_peak", lambda dev, iters: (36.7, 1.0))
+    monkeypatch.delenv("WORLD_SIZE", raising=False)
+    monkeypatch.delenv("RANK", raising=False)
+    args = types.SimpleNamespace(gpus=1, steps=2, warmup=1, impl="ours", config="C4", n=20000,
+                                 no_cpu_baseline=True, no_e2e=False, time_scaling=1e-9)
+    bench.run_ours(args)
+    lines = [l for l in capsys.readouterr().out.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert (REQUIRED - {"impl"}) <= set(d)
+    assert {"roofline", "gpu_launches", "clocks", "steps_per_s"} <= set(d)
+    rf = d["roofline"]
+    assert {"bound", "achieved", "peak", "unit", "frac", "traffic", "general_pass", "k1_passes"} <= set(rf)
+    assert rf["general_pass"]["ms_per_launch"] == 1.5 and "frac" in rf["general_pass"]
+    assert "of" in rf["k1_passes"] and "chunks uniform" in rf["k1_passes"]
+    assert d["e2e"]["h2d_bytes_per_step"] == 20000 * 66 and d["e2e"]["d2h_bytes_per_step"] == 20000 * 61
+    assert d["gpu_launches"] == 10 and d["n_gpus"] == 1 and d["cpu_baseline"] is None
+    assert StubSim.created == 2 and "NB_UNIFORM_TILES" not in os.environ   # the side measurement cleaned up
+    assert np.isclose(d["value"], 20000 * 19999 * 2 / (2 * 2.0e-3))

@@ -1,6 +1,6 @@
 """CPU model of K1's seed refinement (nb_force.cu: w_from_seed, w_from_seed_uni): from a
 MUFU.RSQ64H-like seed y0 = d2^(-1/2) (1 + delta) — high word only, |delta| up to 2^-20 — the seven
-(six) FP64 instructions must deliver m_j d2^(-3/2) to a few ulp.  Emulated with exactly rounded
+(six) FP64 instructions must deliver m_j d2^(-3/2) to < 3 ulp.  Emulated with exactly rounded
 arithmetic (one rounding per __dmul_rn / __fma_rn, as compiled with -fmad=false) against a 200-bit
 reference.  This is the accuracy budget behind the 1e-12 force tolerance (measured on the device:
 3e-16 normwise)."""
@@ -62,17 +62,19 @@ case = st.tuples(st.floats(1e-20, 1e40), st.floats(-2.0 ** -20, 2.0 ** -20), st.
 
 @settings(max_examples=1500, deadline=None)
 @given(case)
-def test_cubic_refinement_delivers_a_few_ulp(c):
+def test_cubic_refinement_delivers_under_three_ulp(c):
     d2, delta, mj = c
     y0 = seed(d2, delta)
     exact = mp.mpf(mj) * mp.mpf(d2) ** mp.mpf(-1.5)
     w = w_from_seed(y0, d2, mj)
-    assert abs((mp.mpf(w) - exact) / exact) <= 4.5e-16
+    # worst case by rounding analysis: 4 roundings of 2^-53 on the product chain, half of u's (the
+    # correction c undoes the rest), c's own, the cubic's truncation: < 5.2e-16; observed <= 4e-16
+    assert abs((mp.mpf(w) - exact) / exact) <= 6e-16
     wu = w_from_seed_uni(y0, d2)
     exact_u = mp.mpf(d2) ** mp.mpf(-1.5)
-    assert abs((mp.mpf(wu) - exact_u) / exact_u) <= 4.5e-16
+    assert abs((mp.mpf(wu) - exact_u) / exact_u) <= 6e-16
     # hoisting the mass costs one more rounding at most: m * w_uni vs the per-pair product
-    assert abs((mp.mpf(dmul(mj, wu)) - exact) / exact) <= 5.6e-16
+    assert abs((mp.mpf(dmul(mj, wu)) - exact) / exact) <= 7.2e-16
 
 
 def test_truncation_error_of_the_cubic_is_far_below_an_ulp_at_the_seed_accuracy():
@@ -88,4 +90,4 @@ def test_truncation_error_of_the_cubic_is_far_below_an_ulp_at_the_seed_accuracy(
     y_garbage = struct.unpack("<d", struct.pack("<Q", bits))[0]
     exact = mp.mpf(mj) * mp.mpf(d2) ** mp.mpf(-1.5)
     for y in (y_hi, y_garbage):
-        assert abs((mp.mpf(w_from_seed(y, d2, mj)) - exact) / exact) <= 4.5e-16
+        assert abs((mp.mpf(w_from_seed(y, d2, mj)) - exact) / exact) <= 6e-16

@@ -43,6 +43,8 @@ def parse():
     ap.add_argument("--bodies", dest="n", type=int, default=0, help="override the body count (development only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extra-configs", action="store_true", help="skip the C2/C3/C5 lines of the `configs` array")
+    ap.add_argument("--no-parity-check", action="store_true", help="skip the untimed sharded-vs-1-GPU self-check")
     ap.add_argument("--time-scaling", type=float, default=1e-9)
     return ap.parse_args()
 
@@ -93,6 +95,25 @@ class ClockSampler:
         return out
 
 
+WORKLOADS = {
+    "C1": "reference sphere-cloud sim geometry (Sim3: sun + two clusters), elastic collisions",
+    "C2": "uniform sphere, per-body masses, collisions off (pure all-pairs force + integrate)",
+    "C3": "cube cloud, elastic collisions",
+    "C3dense": "cube cloud with 4x radii (collision-dense), elastic collisions",
+    "C4": "uniform sphere, elastic collisions",
+}
+SEEDS = {"C1": 11, "C2": 1, "C3": 2, "C3dense": 2, "C4": 3}
+
+
+def workload_config(name: str, n: int, world: int, ts: float):
+    """The `config` object of the JSON line — identical in both arms (ours / --impl reference)."""
+    return {"workload": f"{name}: {n}-body {WORKLOADS.get(name, name)}, one full cycle "
+                        "(force+detect+resolve+integrate)",
+            "n_bodies": n, "parallelism": f"i-shard x{world}", "seed": SEEDS.get(name),
+            "time_scaling": ts, "R": 1.0,
+            "l2": "GPU arm: flushed between timed steps (256 MiB write)"}
+
+
 # ---------------------------------------------------------------- CPU legs (oracle = test infrastructure)
 def cpu_pool_rate(bodies, seconds_target: float, workers: int):
     """Times the work-pool port (oracle/, kind 'port') on a bounded i-slice of the workload.
@@ -141,16 +162,26 @@ def run_reference(args):
         _, sample, rows, dt = cpu_pool_rate(bodies, per_step_s, workers)
         tot_rows += rows
         tot_dt += dt
-    value = tot_rows * (n - 1) / tot_dt
+    # Body.Update over the whole array (O(n), once per cycle) timed for real and added to the extrapolated
+    # cycle; ProcessMods handles ~1e3 events per cycle at C4 (microseconds) and is not in the sample
+    from oracle.oracle import OracleSim
+    ou = OracleSim(bodies.copy())
+    t0 = time.perf_counter()
+    ou.update(args.time_scaling, 1.0)
+    t_update = time.perf_counter() - t0
+    t_cycle = n * (n - 1.0) * tot_dt / (tot_rows * (n - 1.0)) + t_update
+    value = n * (n - 1.0) / t_cycle
     line = {
         "impl": "reference", "metric": "fp64 body-pair interactions/s", "value": value, "unit": "interactions/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * n * (n - 1) / value, "higher_is_better": True, "scaling": "strong",
+        "ms_per_step": 1e3 * t_cycle, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"{args.config}: {n}-body uniform sphere, elastic collisions", "n_bodies": n,
-                   "note": "each step is a bounded i-slice of the workload; ms_per_step is the O(N^2) extrapolation "
-                           "to a full cycle"},
-        "steps_per_s": value / (n * (n - 1.0)),
+        "config": workload_config(args.config, n, args.gpus, args.time_scaling),
+        "note": "the Go reference cannot be built here (no Go toolchain): this is the C port of its goroutine work "
+                "pool (oracle/, contiguous slices over all host threads).  Each step is a bounded i-slice of the "
+                "workload (Body.Compute: force sweep + collision sweep); ms_per_step is the O(N^2) extrapolation "
+                f"to a full cycle plus Body.Update over all bodies measured for real ({1e3 * t_update:.1f} ms)",
+        "steps_per_s": 1.0 / t_cycle,
         "cpu_baseline": {"value": value, "unit": "interactions/s", "cores": workers, "kind": "port",
                          "sample": sample + f" per step, {args.steps} steps"},
         "e2e": {"value": value, "unit": "interactions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -160,16 +191,25 @@ def run_reference(args):
 
 
 def ncu_traffic(n: int, world: int):
-    """dram__bytes_read.sum + dram__bytes_write.sum of one k_force launch from the committed
-    `ncu --set full` capture of the same workload (profiles/r1_k_force_traffic.json), else None."""
+    """(dram__bytes_read.sum + dram__bytes_write.sum of one K1 launch, where that number comes from): read from
+    the committed `ncu --set full` capture of the same workload and kernel instantiation
+    (profiles/r2_k_force_traffic.json) — bench.py itself never runs under a profiler."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r1_k_force_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r2_k_force_traffic.json")) as f:
             for rec in json.load(f):
                 if rec["n_bodies"] == n and rec["n_gpus"] == world:
-                    return rec["dram_bytes_per_launch"]
+                    return rec["dram_bytes_per_launch"], f"profiles/{rec['report']} ({rec['kernel']}), not measured in this run"
     except (OSError, ValueError, KeyError):
         pass
-    return None
+    return None, None
+
+
+def digest(*arrays) -> str:
+    import hashlib
+    h = hashlib.sha256()
+    for a in arrays:
+        h.update(np.ascontiguousarray(a).tobytes())
+    return h.hexdigest()
 
 
 # ---------------------------------------------------------------- our arm
@@ -199,65 +239,129 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    bodies = clouds.config(args.config, n=args.n or None)   # same seed on every rank
-    n = bodies.n
-    sim = capi.Sim(n, device=local)
-    sim.upload(bodies)
-    if world > 1:
+    def new_sim(bodies, shard_upload=False):
+        """One handle per rank holding `bodies`, joined into a communicator when world > 1."""
+        sim = capi.Sim(bodies.n, device=local)
+        if world == 1:
+            sim.upload(bodies)
+            return sim
         uid = [capi.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
+        if not shard_upload:
+            sim.upload(bodies)
         sim.comm_init(rank, world, uid[0])
+        return sim
+
     ts, R = args.time_scaling, 1.0
     # the roofline of K1 needs the CUDA events around it (nb_step_result.ms_force)
     opts = capi.STEP_DEFAULT | capi.STEP_PHASE_TIMINGS
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+    interactions_of = lambda n_: float(n_) * (n_ - 1.0)
+
+    def timed_cycles(sim, steps, warmup):
+        """`warmup` untimed cycles, then `steps` cycles timed by the CUDA events the library records on its
+        own stream around nb_step (L2 flushed before each); returns max-over-ranks seconds and per-phase means."""
+        for _ in range(warmup):
+            sim.step(ts, R, opts)
+        barrier()
+        acc = dict(total=[], force=[], exchange=[], resolve=[], integrate=[], pairs=0, rounds=0)
+        for _ in range(steps):
+            flush.zero_()
+            torch.cuda.synchronize()
+            res = sim.step(ts, R, opts)
+            acc["total"].append(res.ms_total); acc["force"].append(res.ms_force)
+            acc["exchange"].append(res.ms_exchange); acc["resolve"].append(res.ms_resolve)
+            acc["integrate"].append(res.ms_integrate)
+            acc["pairs"] += res.n_pairs
+            acc["rounds"] = max(acc["rounds"], res.resolve_rounds)
+        barrier()
+        if steps:
+            acc["t_dev"] = max_over_ranks(sum(acc["total"]) * 1e-3)
+            acc["t_force"] = max_over_ranks(float(np.mean(acc["force"])) * 1e-3)
+        return acc
+
+    bodies = clouds.config(args.config, n=args.n or None)   # same seed on every rank
+    n = bodies.n
+    sim = new_sim(bodies)
+    interactions = interactions_of(n)
 
     # fp64 roofline denominator measured on this device (MEASURED_PEAKS.json has no fp64 entry)
     peak_burst, _ = capi.measure_fp64_peak(local, 2048)
     barrier()
-    for _ in range(args.warmup):
+
+    # ---- parity self-check (world > 1, untimed): the first sharded cycle against one GPU ----------------
+    # Every rank digests the forces of its shard, the gathered pair list and the whole state after the cycle;
+    # rank 0 steps a single-GPU handle from the same initial state and compares (bit equality through SHA-256).
+    # The driver's GPU test box has one GPU, so this is where the sharded cycle is checked at every N.
+    parity = None
+    warm_done = 0
+    if world > 1 and not args.no_parity_check:
         sim.step(ts, R, opts)
-    barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
+        warm_done = 1
+        i0, i1 = sim.shard_range()
+        fx, fy, fz = sim.forces()
+        st = sim.download()
+        mine = {"i0": i0, "i1": i1, "force": digest(fx[i0:i1], fy[i0:i1], fz[i0:i1]), "pairs": digest(sim.pairs()),
+                "state": digest(st.x, st.y, st.z, st.vx, st.vy, st.vz, st.mass, st.rest, st.flags, st.behavior)}
+        del fx, fy, fz, st
+        got = [None] * world
+        dist.gather_object(mine, got if rank == 0 else None, dst=0)
+        if rank == 0:
+            ref = capi.Sim(n, device=local)
+            ref.upload(bodies)
+            ref.step(ts, R, opts)
+            rfx, rfy, rfz = ref.forces()
+            rst = ref.download()
+            r_pairs = digest(ref.pairs())
+            r_state = digest(rst.x, rst.y, rst.z, rst.vx, rst.vy, rst.vz, rst.mass, rst.rest, rst.flags, rst.behavior)
+            parity = {
+                "force_bits_equal": all(g["force"] == digest(rfx[g["i0"]:g["i1"]], rfy[g["i0"]:g["i1"]],
+                                                             rfz[g["i0"]:g["i1"]]) for g in got),
+                "pairs_equal": all(g["pairs"] == r_pairs for g in got),
+                "state_bits_equal": all(g["state"] == r_state for g in got),
+                "ranks_checked": world, "n_pairs": int(len(ref.pairs())),
+                "what": "cycle 1 from the uploaded state: each rank's shard forces, gathered pair list and full state "
+                        "(x..vz, mass, rest, flags, behavior) vs a single-GPU handle on rank 0, SHA-256 of the raw bytes",
+            }
+            ref.close()
+            del rfx, rfy, rfz, rst
+        barrier()
+
+    timed_cycles(sim, 0, max(args.warmup - warm_done, 0))      # the remaining warm-up cycles
+    sampler = ClockSampler(local) if rank == 0 else None       # clocks / throttle reasons DURING the timed region
     launches0 = sim.launch_count()
-    ms_steps, ms_force, pairs_seen, rounds = [], [], 0, 0
     t_wall0 = time.perf_counter()
-    for _ in range(args.steps):
-        flush.zero_()
-        torch.cuda.synchronize()
-        res = sim.step(ts, R, opts)          # CUDA events on the library's stream bracket the step
-        ms_steps.append(res.ms_total)
-        ms_force.append(res.ms_force)
-        pairs_seen += res.n_pairs
-        rounds = max(rounds, res.resolve_rounds)
-    barrier()
+    acc = timed_cycles(sim, args.steps, 0)
     t_wall = time.perf_counter() - t_wall0
     launches = sim.launch_count() - launches0
     clocks = sampler.stop() if sampler else None
-    t_dev = max_over_ranks(sum(ms_steps) * 1e-3)
-    t_force = max_over_ranks(float(np.mean(ms_force)) * 1e-3)
-    interactions = float(n) * (n - 1.0)
+    t_dev, t_force = acc["t_dev"], acc["t_force"]
     value = interactions * args.steps / t_dev
     peak_sust, _ = capi.measure_fp64_peak(local, 1 << 15)   # ~1 s back-to-back DFMA under the power cap
+    mode = capi.COMM_MODE_NAMES.get(sim.comm_mode(), "?")
 
-    # ---- e2e: host buffers through the C ABI every step -----------------------------------
+    # ---- e2e: host buffers through the C ABI every step ---------------------------------------------------
+    # Every rank moves only its own i-range over its host link (nb_upload_shard / nb_download_*_range): the other
+    # ranks' slices arrive over NVLink inside the upload, and after the cycle every rank returns its own slice.
     e2e = None
     if not args.no_e2e:
+        i0, i1, _, _ = capi.plan(n, rank, world)
+        cnt = i1 - i0
         names = ("x", "y", "z", "vx", "vy", "vz", "mass", "radius")
-        pinned = {k: torch.empty(n, dtype=torch.float64).pin_memory().numpy() for k in names}
+        pinned = {k: torch.empty(cnt, dtype=torch.float64).pin_memory().numpy() for k in names}
         for k in names:
-            pinned[k][:] = getattr(bodies, k)
-        beh = torch.empty(n, dtype=torch.uint8).pin_memory().numpy(); beh[:] = bodies.behavior
-        flg = torch.empty(n, dtype=torch.uint8).pin_memory().numpy(); flg[:] = bodies.flags
-        out = {k: torch.empty(n, dtype=torch.float64).pin_memory().numpy() for k in names[:6]}
-        rxyz = torch.empty((n, 3), dtype=torch.float32).pin_memory().numpy()
-        rex = torch.empty(n, dtype=torch.uint8).pin_memory().numpy()
+            pinned[k][:] = getattr(bodies, k)[i0:i1]
+        beh = torch.empty(cnt, dtype=torch.uint8).pin_memory().numpy(); beh[:] = bodies.behavior[i0:i1]
+        flg = torch.empty(cnt, dtype=torch.uint8).pin_memory().numpy(); flg[:] = bodies.flags[i0:i1]
+        out = {k: torch.empty(cnt, dtype=torch.float64).pin_memory().numpy() for k in names[:6]}
+        rxyz = torch.empty((cnt, 3), dtype=torch.float32).pin_memory().numpy()
+        rex = torch.empty(cnt, dtype=torch.uint8).pin_memory().numpy()
 
         def e2e_step():
-            sim.upload_raw(n, *[pinned[k] for k in names], behavior=beh, flags=flg)
+            sim.upload_shard(n, i0, cnt, *[pinned[k] for k in names], behavior=beh, flags=flg)
             sim.step(ts, R, opts)
-            sim.download_into(**out)
-            sim.render(rxyz, rex)
+            sim.download_range_into(i0, cnt, **out)
+            sim.render_range(i0, cnt, rxyz, rex)
             for k in names[:6]:          # next cycle starts from the returned state, like the host loop:
                 pinned[k], out[k] = out[k], pinned[k]   # both pinned — swap roles instead of a host memcpy
 
@@ -270,12 +374,15 @@ def run_ours(args):
         t_e2e = max_over_ranks(time.perf_counter() - t0)
         e2e = {"value": interactions * args.steps / t_e2e, "unit": "interactions/s",
                "h2d_bytes_per_step": int(n * (8 * 8 + 2)), "d2h_bytes_per_step": int(n * (6 * 8 + 13)),
-               "ms_per_step": 1e3 * t_e2e / args.steps, "timer": "host perf_counter around synchronous C-ABI calls"}
+               "ms_per_step": 1e3 * t_e2e / args.steps, "timer": "host perf_counter around synchronous C-ABI calls",
+               "path": ("nb_upload_shard -> nb_step -> nb_download_state_range + nb_download_render_range; the byte "
+                        "counts are totals over all ranks (each rank moves its own n/N slice over its host link)")}
+    sim.close()
 
     # ---- K1 with the uniform-mass pass disabled (N=1 only; reported beside the headline) ----
-    # C4's bodies share one mass, so 31 of its 32 j-chunks run K1's uniform-mass instantiation
-    # (DESIGN.md §3).  A collection with mixed masses runs the per-body-mass pass; its K1 time on this
-    # same cloud is measured here, outside every timed region, so that both figures are on record.
+    # C4's bodies share one mass, so its j-chunks run K1's uniform-mass instantiation.  A
+    # collection with mixed masses runs the per-body-mass pass; its K1 time on this same cloud is measured
+    # here, outside every timed region, so that both figures are on record.
     general = None
     if world == 1:
         try:
@@ -292,6 +399,29 @@ def run_ours(args):
             general = {"ms_per_launch": ms_g}
         except Exception as e:   # never let the side measurement cost the bench line
             general = {"error": str(e)}
+
+    # ---- the other BASELINE configs on the same code, same protocol (untimed for the headline) -------------
+    extra = []
+    if not args.no_extra_configs and not args.n:
+        plan = [("C2", None, 30), ("C3", None, 10), ("C3dense", None, 5)]
+        sweep = [1_000, 4_000, 16_000, 64_000, 256_000] + ([4_000_000] if world >= 4 else [])
+        plan += [("C4", m, 30 if m <= 16_000 else (8 if m <= 256_000 else 2)) for m in sweep]
+        for name, m, k in plan:
+            try:
+                b2 = clouds.config(name, n=m)
+                s2 = new_sim(b2)
+                a2 = timed_cycles(s2, k, 3)
+                s2.close()
+                it = interactions_of(b2.n)
+                ach = FLOPS_PER_INTERACTION * (it / world) / a2["t_force"] / 1e12
+                extra.append({"config": ("C5 sweep: " if m else "") + name, "n_bodies": b2.n, "n_gpus": world, "steps": k,
+                              "warmup": 3, "value": it * k / a2["t_dev"], "unit": "interactions/s",
+                              "ms_per_step": 1e3 * a2["t_dev"] / k, "steps_per_s": k / a2["t_dev"],
+                              "ms_force": 1e3 * a2["t_force"], "roofline_frac": ach / peak_burst,
+                              "collision_pairs_per_step": a2["pairs"] / k, "resolve_rounds": a2["rounds"]})
+            except Exception as e:
+                extra.append({"config": name, "n_bodies": m, "error": str(e)})
+            barrier()
 
     # ---- CPU baseline beside it (rank 0, N=1 only) -----------------------------------------
     cpu = None
@@ -314,18 +444,22 @@ def run_ours(args):
             a_g = FLOPS_PER_INTERACTION * local_pairs / (general["ms_per_launch"] * 1e-3) / 1e12
             general.update(achieved=a_g, frac=a_g / peak_burst,
                            note="same launch with NB_UNIFORM_TILES=0: every chunk on the per-body-mass pass")
+        traffic, traffic_source = ncu_traffic(n, world)
+        cfg = workload_config(args.config, n, world, ts)
         line = {
             "metric": "fp64 body-pair interactions/s", "value": value, "unit": "interactions/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{args.config}: {n}-body uniform sphere, elastic collisions, one full cycle "
-                                   "(force+detect+resolve+integrate)", "n_bodies": n, "parallelism": f"i-shard x{world}",
-                       "l2": "flushed between timed steps (256 MiB write)", "seed": 3,
-                       "collision_pairs_per_step": pairs_seen / max(args.steps, 1), "resolve_rounds": rounds},
+            "config": cfg,
+            "run_stats": {"collision_pairs_per_step": acc["pairs"] / max(args.steps, 1), "resolve_rounds": acc["rounds"],
+                          "ms_force": float(np.mean(acc["force"])), "ms_exchange": float(np.mean(acc["exchange"])),
+                          "ms_resolve": float(np.mean(acc["resolve"])), "ms_integrate": float(np.mean(acc["integrate"]))},
+            "exchange": mode, "ms_exchange": float(np.mean(acc["exchange"])),
+            "parity_check": parity,
             "steps_per_s": args.steps / t_dev,
             "wall_s_timed_region": t_wall,
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": peak_burst, "unit": "TFLOP/s",
-                         "frac": achieved / peak_burst, "traffic": ncu_traffic(n, world),
+                         "frac": achieved / peak_burst, "traffic": traffic, "traffic_source": traffic_source,
                          "kernel": "k_force", "peak_source": "measured here: DFMA chain (nb_measure_fp64_peak), burst",
                          "peak_sustained": peak_sust, "frac_of_sustained": achieved / peak_sust,
                          "peak_nominal": NOMINAL_FP64_TFLOPS, "frac_of_nominal": achieved / NOMINAL_FP64_TFLOPS,
@@ -334,9 +468,9 @@ def run_ours(args):
                          "k1_passes": k1_passes,
                          "general_pass": general},
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "configs": extra,
         }
         print(json.dumps(line), flush=True)
-    sim.close()
     if world > 1:
         dist.destroy_process_group()
 

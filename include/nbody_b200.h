@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define NB_ABI_VERSION 2
+#define NB_ABI_VERSION 3
 
 /* ---- error codes ------------------------------------------------------- */
 #define NB_OK 0
@@ -125,6 +125,20 @@ int nb_upload(nb_handle h, int64_t n,
               const double *restitution, const double *frag_factor, const double *frag_step,
               const uint8_t *behavior, const uint8_t *flags);
 
+/* nb_upload for several GPUs without n bodies crossing every host link: each handle passes only
+ * ITS slice — bodies [first, first+count) must be the handle's i-range for n (nb_plan), the array
+ * pointers address that slice — and the slices reach the other handles' replicas over NVLink
+ * (peer stores; NCCL all-gathers in the fallback mode).  Collective: every handle of the
+ * communicator must call it with the same n and the same set of non-NULL arrays.  On a single-GPU
+ * handle it is nb_upload.  The partition it serves is the slice rule of
+ * cmd/runner/computation-runner.go:286-293. */
+int nb_upload_shard(nb_handle h, int64_t n, int64_t first, int64_t count,
+                    const double *x, const double *y, const double *z,
+                    const double *vx, const double *vy, const double *vz,
+                    const double *mass, const double *radius,
+                    const double *restitution, const double *frag_factor, const double *frag_step,
+                    const uint8_t *behavior, const uint8_t *flags);
+
 /* Overwrites bodies [first, first+count) — Body.ApplyMods
  * (cmd/body/body.go:274-313) and SetNotExists (:93-96) for a dirty range.
  * Any array pointer may be NULL (field unchanged). */
@@ -170,6 +184,14 @@ int nb_download_state(nb_handle h,
                       double *x, double *y, double *z, double *vx, double *vy, double *vz,
                       double *mass, double *radius, double *restitution,
                       uint8_t *behavior, uint8_t *flags);
+/* The same for bodies [first, first+count) only.  After a cycle every handle of a communicator
+ * holds the whole state, so a host driving several GPUs lets each handle return its own i-range
+ * (n/P bodies per host link instead of n). */
+int nb_download_state_range(nb_handle h, int64_t first, int64_t count,
+                            double *x, double *y, double *z, double *vx, double *vy, double *vz,
+                            double *mass, double *radius, double *restitution,
+                            uint8_t *behavior, uint8_t *flags);
+int nb_download_render_range(nb_handle h, int64_t first, int64_t count, float *xyz, uint8_t *exists);
 /* Renderable snapshot of the last step (cmd/body/renderable.go:22-40):
  * xyz = 3 floats per body (zeros for !Exists stubs), exists = 1 byte per body. */
 int nb_download_render(nb_handle h, float *xyz, uint8_t *exists);
@@ -201,6 +223,15 @@ int nb_comm_unique_id(void *id128);
  * computation-runner.go:286-293); every rank must make the same sequence of
  * upload/patch/append/compact/step calls with the same arguments. */
 int nb_comm_init(nb_handle h, int rank, int nranks, const void *id128);
+/* How this handle exchanges data with the other handles of its communicator each cycle:
+ * NB_COMM_SINGLE (no communicator), NB_COMM_PEER_PUSH (the kernels store into the peers'
+ * replicas over NVLink: no collective in steady state) or NB_COMM_NCCL (NCCL all-gathers — the
+ * fallback when a peer mapping failed, or NB_PEER_PUSH=0; nb_comm_init also prints a [WARN]
+ * line to stderr when it falls back on its own).  Results are bit-identical in all three. */
+#define NB_COMM_SINGLE 0
+#define NB_COMM_PEER_PUSH 1
+#define NB_COMM_NCCL 2
+int nb_comm_mode(nb_handle h, int *mode);
 /* The i-range [i0,i1) this handle computes. */
 int nb_shard_range(nb_handle h, int64_t *i0, int64_t *i1);
 

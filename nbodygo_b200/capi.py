@@ -26,13 +26,16 @@ STEP_DEFAULT = STEP_COLLISIONS
 
 EV_COLLISION, EV_SUBSUME, EV_FRAGMENT = 0, 1, 2
 
+COMM_SINGLE, COMM_PEER_PUSH, COMM_NCCL = 0, 1, 2
+COMM_MODE_NAMES = {COMM_SINGLE: "single", COMM_PEER_PUSH: "peer_push", COMM_NCCL: "nccl"}
+
 # every symbol include/nbody_b200.h declares (checked by tests/test_capi_symbols.py)
 SYMBOLS = (
     "nb_create", "nb_destroy", "nb_last_error", "nb_abi_version", "nb_upload", "nb_patch", "nb_append",
     "nb_compact", "nb_count", "nb_step", "nb_sync", "nb_download_state", "nb_download_render", "nb_render_buffers",
     "nb_get_forces", "nb_get_pairs", "nb_get_host_events", "nb_comm_unique_id", "nb_comm_init",
     "nb_shard_range", "nb_plan", "nb_measure_fp64_peak", "nb_launch_count",
-    "nb_graph_stats",
+    "nb_graph_stats", "nb_upload_shard", "nb_download_state_range", "nb_download_render_range", "nb_comm_mode",
 )
 
 
@@ -80,6 +83,10 @@ def load(path: str | None = None):
     L.nb_abi_version.argtypes = []
     L.nb_upload.argtypes = [H, C.c_int64] + state_in
     L.nb_patch.argtypes = [H, C.c_int64, C.c_int64] + state_in
+    L.nb_upload_shard.argtypes = [H, C.c_int64, C.c_int64, C.c_int64] + state_in
+    L.nb_download_state_range.argtypes = [H, C.c_int64, C.c_int64] + [_DP] * 9 + [_U8P] * 2
+    L.nb_download_render_range.argtypes = [H, C.c_int64, C.c_int64, C.POINTER(C.c_float), _U8P]
+    L.nb_comm_mode.argtypes = [H, C.POINTER(C.c_int)]
     L.nb_append.argtypes = [H, C.c_int64, C.c_double] + [_DP] * 10 + [_U8P] * 2
     L.nb_compact.argtypes = [H, _I64P, _I64P, C.c_int64]
     L.nb_count.argtypes = [H, _I64P]
@@ -156,6 +163,15 @@ class Sim:
         beh, fl = _u8(behavior), _u8(flags)
         self._chk(self.L.nb_upload(self.h, n, *[_p(a) for a in arrs], _p(beh, _U8P), _p(fl, _U8P)))
 
+    def upload_shard(self, n, first, count, x, y, z, vx, vy, vz, mass, radius, rest=None, ff=None, fs=None,
+                     behavior=None, flags=None):
+        """Collective sharded upload: the arrays hold only this handle's slice [first, first+count) of n bodies."""
+        arrs = [_f64(a) for a in (x, y, z, vx, vy, vz, mass, radius, rest, ff, fs)]
+        beh, fl = _u8(behavior), _u8(flags)
+        for a in arrs + [beh, fl]:
+            assert a is None or len(a) == count
+        self._chk(self.L.nb_upload_shard(self.h, n, first, count, *[_p(a) for a in arrs], _p(beh, _U8P), _p(fl, _U8P)))
+
     def patch(self, first, count, **fields):
         names = ("x", "y", "z", "vx", "vy", "vz", "mass", "radius", "rest", "frag_factor", "frag_step")
         arrs = [_f64(fields.get(f)) for f in names]
@@ -205,6 +221,14 @@ class Sim:
         self._chk(self.L.nb_download_state(self.h, _p(x), _p(y), _p(z), _p(vx), _p(vy), _p(vz),
                                            None, None, None, None, None))
 
+    def download_range_into(self, first, count, x=None, y=None, z=None, vx=None, vy=None, vz=None):
+        self._chk(self.L.nb_download_state_range(self.h, first, count, _p(x), _p(y), _p(z), _p(vx), _p(vy), _p(vz),
+                                                 None, None, None, None, None))
+
+    def render_range(self, first, count, xyz, exists):
+        self._chk(self.L.nb_download_render_range(self.h, first, count, xyz.ctypes.data_as(C.POINTER(C.c_float)),
+                                                  _p(exists, _U8P)))
+
     def render(self, xyz=None, exists=None):
         n = self.count()
         xyz = np.zeros((n, 3), dtype=np.float32) if xyz is None else xyz
@@ -247,6 +271,12 @@ class Sim:
         buf = C.create_string_buffer(uid, 128)
         self._chk(self.L.nb_comm_init(self.h, rank, nranks, buf))
 
+    def comm_mode(self) -> int:
+        """COMM_SINGLE, COMM_PEER_PUSH (kernels store into the peers' replicas) or COMM_NCCL (all-gathers)."""
+        m = C.c_int(-1)
+        self._chk(self.L.nb_comm_mode(self.h, C.byref(m)))
+        return m.value
+
     def shard_range(self):
         a, b = C.c_int64(0), C.c_int64(0)
         self._chk(self.L.nb_shard_range(self.h, C.byref(a), C.byref(b)))
@@ -277,7 +307,9 @@ def plan(n: int, rank: int = 0, nranks: int = 1):
 def uniform_chunks(b: BodyArrays):
     """(uniform j-chunks, j-chunks, uniform tiles, tiles) of K1 for this collection — the host-side
     mirror of K0's `tile_muni` rule and K1's per-chunk dispatch (nb_force.cu), for reports and tests:
-    a tile is uniform if all its slots hold live, non-fragmenting bodies of one positive finite mass;
+    a tile is uniform if all its LIVE bodies have one positive finite mass (slots without a live body
+    — bodies that do not exist, non-finite positions, the tail of the last tile — are parked far away
+    and match any mass; a fragmenting body stays in place with effective mass 0 and breaks it);
     a chunk runs the uniform-mass pass if all its tiles are.  Collections below 16,384 bodies use
     64-body tiles and a single per-body-mass launch (returns 0 uniform chunks for them)."""
     from .bodies import F_EXISTS, F_FRAGMENTING
@@ -285,12 +317,18 @@ def uniform_chunks(b: BodyArrays):
     _, _, n_chunks, tpc = plan(n)
     tj = 64 if n < 16384 else 256
     n_tiles = (n + tj - 1) // tj
-    m = np.zeros(n_tiles * tj)
-    live = ((b.flags & F_EXISTS) != 0) & ((b.flags & F_FRAGMENTING) == 0)
-    m[:n] = np.where(live, b.mass, 0.0)
-    m = m.reshape(n_tiles, tj)
     with np.errstate(invalid="ignore"):
-        ok = np.all((m > 0) & (m < np.inf), axis=1) & (m.min(axis=1) == m.max(axis=1))
+        finite = (np.abs(b.x) < 1e150) & (np.abs(b.y) < 1e150) & (np.abs(b.z) < 1e150)
+    live = np.zeros(n_tiles * tj, dtype=bool)
+    live[:n] = ((b.flags & F_EXISTS) != 0) & finite
+    m = np.zeros(n_tiles * tj)
+    m[:n] = np.where((b.flags & F_FRAGMENTING) == 0, b.mass, 0.0)
+    live, m = live.reshape(n_tiles, tj), m.reshape(n_tiles, tj)
+    with np.errstate(invalid="ignore"):
+        odd = np.any(live & ~((m > 0) & (m < np.inf)), axis=1)
+        lo = np.where(live, m, np.inf).min(axis=1)
+        hi = np.where(live, m, 0.0).max(axis=1)
+    ok = ~odd & ((lo == hi) | (hi == 0.0))
     if tj == 64:
         return 0, n_chunks, int(ok.sum()), n_tiles
     pad = np.ones(n_chunks * tpc, dtype=bool)

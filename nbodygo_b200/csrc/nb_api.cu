@@ -98,6 +98,7 @@ struct nb_sim {
     PeerTable *d_peers = nullptr;
     unsigned long long *d_sync = nullptr;  // my flag block: 2*MAX_RANKS slots
     unsigned long long step_id = 0;
+    unsigned long long upload_id = 0;  // sharded uploads so far (flag value of the PEER_SLOT_UP_* rounds)
     int2 *pairs_all_base = nullptr;
     std::vector<void *> ipc_opened;
     // library-owned pinned host buffers that every step fills with the Renderable snapshot
@@ -167,7 +168,7 @@ static void free_all(nb_handle h)
     for (int k = 0; k < N_F64; ++k) cudaFree(*f64_fields(h->d, k));
     cudaFree(h->d.jx); cudaFree(h->d.jy); cudaFree(h->d.jz);
     cudaFree(h->d.jm); cudaFree(h->d.m0); cudaFree(h->d.computes0); cudaFree(h->d.fx); cudaFree(h->d.fy); cudaFree(h->d.fz);
-    cudaFree(h->d.behavior); cudaFree(h->d.flags); cudaFree(h->d.tile_rmax); cudaFree(h->d.tile_muni);
+    cudaFree(h->d.behavior); cudaFree(h->d.flags); cudaFree(h->d.tile_rmax); cudaFree(h->d.tile_muni); cudaFree(h->d.tile_dead);
     cudaFree(h->d.px); cudaFree(h->d.py); cudaFree(h->d.pz);
     cudaFree(h->d.render); cudaFree(h->d.render_exists);
     if (h->d.pairs_all != h->d.pairs) cudaFree(h->d.pairs_all);
@@ -269,6 +270,8 @@ extern "C" int nb_create(int device, int64_t capacity, int64_t pair_capacity, nb
     NB_TRY(cudaMalloc((void **)&h->d.tile_rmax, (size_t)(h->cap_pad / TJ_SMALL) * sizeof(double)));
     NB_TRY(cudaMalloc((void **)&h->d.tile_muni, (size_t)(h->cap_pad / TJ_SMALL) * sizeof(double)));
     NB_TRY(cudaMemsetAsync(h->d.tile_muni, 0, (size_t)(h->cap_pad / TJ_SMALL) * sizeof(double), h->st));
+    NB_TRY(cudaMalloc((void **)&h->d.tile_dead, (size_t)(h->cap_pad / TJ_SMALL)));
+    NB_TRY(cudaMemsetAsync(h->d.tile_dead, 0, (size_t)(h->cap_pad / TJ_SMALL), h->st));
     NB_TRY(cudaMalloc((void **)&h->d.render, (size_t)h->cap_pad * 3 * sizeof(float)));
     NB_TRY(cudaMalloc((void **)&h->d.render_exists, (size_t)h->cap_pad));
     NB_TRY(cudaMemsetAsync(h->d.render, 0, (size_t)h->cap_pad * 3 * sizeof(float), h->st));
@@ -312,6 +315,8 @@ extern "C" int nb_destroy(nb_handle h)
 }
 
 // ---------------------------------------------------------------- state sync
+static int finish_step(nb_handle h, nb_step_result *out);
+
 static int copy_in_f64(nb_handle h, double *dst, const double *src, long long first, long long count, double dflt,
                        bool use_default)
 {
@@ -372,6 +377,98 @@ extern "C" int nb_upload(nb_handle h, int64_t n, const double *x, const double *
     h->stepped = false;
     return write_range(h, 0, n, true, 1.0, x, y, z, vx, vy, vz, mass, radius, restitution, frag_factor, frag_step,
                        behavior, flags);
+}
+
+// Sharded variant of nb_upload for several GPUs: every rank passes only ITS slice of the array (the
+// i-range nb_plan gives for n) and the slices reach the other ranks' replicas over NVLink instead of
+// n bodies crossing every rank's host link.  Collective: every rank calls it with the same n.
+extern "C" int nb_upload_shard(nb_handle h, int64_t n, int64_t first, int64_t count, const double *x, const double *y,
+                               const double *z, const double *vx, const double *vy, const double *vz,
+                               const double *mass, const double *radius, const double *restitution,
+                               const double *frag_factor, const double *frag_step, const uint8_t *behavior,
+                               const uint8_t *flags)
+{
+    if (!h || n < 0) return fail(h, NB_ERR_INVALID, "nb_upload_shard: bad arguments");
+    if (n > h->cap) return fail(h, NB_ERR_CAPACITY, "nb_upload_shard: n exceeds capacity");
+    const long long shard = (n + h->nranks - 1) / h->nranks;
+    const long long i0 = std::min<long long>(n, (long long)h->rank * shard), i1 = std::min<long long>(n, i0 + shard);
+    if (first != i0 || count != i1 - i0)
+        return fail(h, NB_ERR_INVALID, "nb_upload_shard: [first, first+count) must be this handle's i-range (nb_plan)");
+    if (count > 0 && (!x || !y || !z || !vx || !vy || !vz || !mass || !radius))
+        return fail(h, NB_ERR_INVALID, "nb_upload_shard: x,y,z,vx,vy,vz,mass,radius are required");
+    if (h->pending) {
+        int rc = finish_step(h, nullptr);
+        if (rc) return rc;
+    }
+    NB_CUDA(h, cudaSetDevice(h->device));
+    h->n = n;
+    h->stepped = false;
+    if (h->nranks == 1)
+        return write_range(h, 0, n, true, 1.0, x, y, z, vx, vy, vz, mass, radius, restitution, frag_factor, frag_step,
+                           behavior, flags);
+    StepParams p{};
+    p.s = h->d;
+    p.peers = h->d_peers;
+    p.n = n; p.i0 = i0; p.i1 = i1;
+    p.rank = h->rank; p.nranks = h->nranks;
+    p.step_id = ++h->upload_id;
+    if (h->peer_push) {
+        // nobody may write into my replica while a kernel of my last cycle still reads it (the render
+        // snapshot of k_count_dead), and vice versa: one flag round before the slices move
+        h->launches += launch_peer_signal(p, PEER_SLOT_UP_READY, h->st);
+        h->launches += launch_peer_wait(p, PEER_SLOT_UP_READY, h->st);
+    }
+    const double *src[N_F64] = {x, y, z, vx, vy, vz, mass, radius, restitution, frag_factor, frag_step};
+    const double dfl[N_F64] = {0, 0, 0, 0, 0, 0, 0, 0, 1.0, 0, 0};
+    unsigned mask = 0;
+    for (int k = 0; k < N_F64; ++k) {
+        double *dst = *f64_fields(h->d, k);
+        if (src[k]) {
+            if (count > 0)
+                NB_CUDA(h, cudaMemcpyAsync(dst + i0, src[k], (size_t)count * sizeof(double), cudaMemcpyHostToDevice, h->st));
+            mask |= 1u << k;
+        } else {
+            h->launches += launch_fill_f64(dst, dfl[k], n, h->st);  // defaults need no exchange
+        }
+    }
+    if (behavior) {
+        if (count > 0) NB_CUDA(h, cudaMemcpyAsync(h->d.behavior + i0, behavior, (size_t)count, cudaMemcpyHostToDevice, h->st));
+        mask |= PUSH_BEHAVIOR;
+    } else {
+        h->launches += launch_fill_u8(h->d.behavior, NB_ELASTIC, n, h->st);
+    }
+    if (flags) {
+        if (count > 0) NB_CUDA(h, cudaMemcpyAsync(h->d.flags + i0, flags, (size_t)count, cudaMemcpyHostToDevice, h->st));
+        mask |= PUSH_FLAGS;
+    } else {
+        h->launches += launch_fill_u8(h->d.flags, NB_F_EXISTS, n, h->st);
+    }
+    for (double *f : {h->d.fx, h->d.fy, h->d.fz})  // NewBody, body.go:73-75
+        NB_CUDA(h, cudaMemsetAsync(f, 0, (size_t)n * sizeof(double), h->st));
+    if (h->peer_push) {
+        h->launches += launch_push_shard(p, mask, h->st);
+        h->launches += launch_peer_signal(p, PEER_SLOT_UP_ARRIVED, h->st);
+        h->launches += launch_peer_wait(p, PEER_SLOT_UP_ARRIVED, h->st);
+    } else {
+        NB_NCCL(h, g_nccl.GroupStart());
+        for (int k = 0; k < N_F64; ++k) {
+            if (!(mask & (1u << k))) continue;
+            double *a = *f64_fields(h->d, k);
+            NB_NCCL(h, g_nccl.AllGather(a + (long long)h->rank * shard, a, (size_t)shard, NCCL_FLOAT64, h->comm, h->st));
+        }
+        if (mask & PUSH_BEHAVIOR)
+            NB_NCCL(h, g_nccl.AllGather(h->d.behavior + (long long)h->rank * shard, h->d.behavior, (size_t)shard,
+                                        NCCL_UINT8, h->comm, h->st));
+        if (mask & PUSH_FLAGS)
+            NB_NCCL(h, g_nccl.AllGather(h->d.flags + (long long)h->rank * shard, h->d.flags, (size_t)shard, NCCL_UINT8,
+                                        h->comm, h->st));
+        NB_NCCL(h, g_nccl.GroupEnd());
+    }
+    // host buffers may be reused by the caller as soon as we return; the peers' slices have landed
+    NB_CUDA(h, cudaStreamSynchronize(h->st));
+    NB_CUDA(h, cudaMemcpy(h->h_ctr, h->d.ctr, sizeof(Counters), cudaMemcpyDeviceToHost));
+    if (h->h_ctr->peer_timeout) return fail(h, NB_ERR_COMM, "sharded upload timed out: a rank did not join it");
+    return NB_OK;
 }
 
 extern "C" int nb_patch(nb_handle h, int64_t first, int64_t count, const double *x, const double *y, const double *z,
@@ -604,6 +701,11 @@ static int enqueue_cycle(nb_handle h, StepParams &p, uint32_t opts, bool capturi
                 for (double *a : arrs)
                     NB_NCCL(h, g_nccl.AllGather(a + (long long)h->rank * shard, a, (size_t)shard, NCCL_FLOAT64,
                                                 h->comm, h->st));
+                // Body.fx,fy,fz: read back only for bodies that do not compute (fragmenting), whose owner may
+                // change when Cycle moves the shard boundaries
+                for (double *a : {h->d.fx, h->d.fy, h->d.fz})
+                    NB_NCCL(h, g_nccl.AllGather(a + (long long)h->rank * shard, a, (size_t)shard, NCCL_FLOAT64,
+                                                h->comm, h->st));
                 NB_NCCL(h, g_nccl.AllGather(h->d.flags + (long long)h->rank * shard, h->d.flags, (size_t)shard,
                                             NCCL_UINT8, h->comm, h->st));
                 NB_NCCL(h, g_nccl.GroupEnd());
@@ -744,6 +846,41 @@ extern "C" int nb_download_state(nb_handle h, double *x, double *y, double *z, d
     return NB_OK;
 }
 
+// Range variant: bodies [first, first+count) only.  On several GPUs every handle holds the whole state
+// after a cycle, so a host that wants each GPU to return its own slice (n/P bodies per host link)
+// passes the handle's i-range here.
+extern "C" int nb_download_state_range(nb_handle h, int64_t first, int64_t count, double *x, double *y, double *z,
+                                       double *vx, double *vy, double *vz, double *mass, double *radius,
+                                       double *restitution, uint8_t *behavior, uint8_t *flags)
+{
+    if (!h || first < 0 || count < 0 || first + count > h->n) return fail(h, NB_ERR_INVALID, "nb_download_state_range: bad range");
+    NB_CUDA(h, cudaSetDevice(h->device));
+    const size_t fb = (size_t)count * sizeof(double);
+    double *dst[] = {x, y, z, vx, vy, vz, mass, radius, restitution};
+    for (int k = 0; k < 9; ++k) {
+        int rc = copy_out(h, dst[k], *f64_fields(h->d, k) + first, fb);
+        if (rc) return rc;
+    }
+    int rc = copy_out(h, behavior, h->d.behavior + first, (size_t)count);
+    if (rc) return rc;
+    rc = copy_out(h, flags, h->d.flags + first, (size_t)count);
+    if (rc) return rc;
+    NB_CUDA(h, cudaStreamSynchronize(h->st));
+    return NB_OK;
+}
+
+extern "C" int nb_download_render_range(nb_handle h, int64_t first, int64_t count, float *xyz, uint8_t *exists)
+{
+    if (!h || first < 0 || count < 0 || first + count > h->n) return fail(h, NB_ERR_INVALID, "nb_download_render_range: bad range");
+    NB_CUDA(h, cudaSetDevice(h->device));
+    int rc = copy_out(h, xyz, h->d.render + 3 * first, (size_t)count * 3 * sizeof(float));
+    if (rc) return rc;
+    rc = copy_out(h, exists, h->d.render_exists + first, (size_t)count);
+    if (rc) return rc;
+    NB_CUDA(h, cudaStreamSynchronize(h->st));
+    return NB_OK;
+}
+
 extern "C" int nb_download_render(nb_handle h, float *xyz, uint8_t *exists)
 {
     if (!h) return NB_ERR_INVALID;
@@ -858,8 +995,8 @@ extern "C" int nb_comm_unique_id(void *id128)
 // agree on the outcome: if any rank cannot map a peer, everybody falls back to the NCCL all-gather.
 namespace {
 struct PeerInfo {
-    cudaIpcMemHandle_t ipc[11];
-    unsigned long long raw[11];
+    cudaIpcMemHandle_t ipc[PEER_ARRAYS];
+    unsigned long long raw[PEER_ARRAYS];
     long long pid;
     int device, ok;
 };
@@ -880,15 +1017,16 @@ static int setup_peer_push(nb_handle h)
     NB_CUDA(h, cudaMalloc((void **)&h->d_pair_counts, 2 * MAX_RANKS * sizeof(unsigned long long)));
     NB_CUDA(h, cudaMemset(h->d_pair_counts, 0, 2 * MAX_RANKS * sizeof(unsigned long long)));
     h->pairs_all_base = h->d.pairs_all;
-    void *mine[11] = {h->d.x, h->d.y, h->d.z, h->d.vx, h->d.vy, h->d.vz, h->d.rest, h->d.flags, h->d_sync,
-                      h->d.pairs_all, h->d_pair_counts};
+    void *mine[PEER_ARRAYS] = {h->d.x, h->d.y, h->d.z, h->d.vx, h->d.vy, h->d.vz, h->d.rest, h->d.flags, h->d_sync,
+                               h->d.pairs_all, h->d_pair_counts, h->d.fx, h->d.fy, h->d.fz, h->d.mass, h->d.radius,
+                               h->d.ff, h->d.fs, h->d.behavior};
     std::vector<PeerInfo> info((size_t)P);
     PeerInfo &me = info[(size_t)h->rank];
     memset(&me, 0, sizeof me);
     me.ok = 1;
     me.pid = (long long)getpid();
     me.device = h->device;
-    for (int k = 0; k < 11; ++k) {
+    for (int k = 0; k < PEER_ARRAYS; ++k) {
         me.raw[k] = (unsigned long long)(uintptr_t)mine[k];
         if (cudaIpcGetMemHandle(&me.ipc[k], mine[k]) != cudaSuccess) { me.ok = 0; cudaGetLastError(); }
     }
@@ -907,12 +1045,13 @@ static int setup_peer_push(nb_handle h)
     memset(&t, 0, sizeof t);
     int ok = 1;
     for (int q = 0; q < P && ok; ++q) ok = info[(size_t)q].ok;
-    void **slots[11] = {(void **)t.x, (void **)t.y, (void **)t.z, (void **)t.vx, (void **)t.vy, (void **)t.vz,
-                        (void **)t.rest, (void **)t.flags, (void **)t.sync, (void **)t.pairs_all,
-                        (void **)t.pair_counts};
+    void **slots[PEER_ARRAYS] = {(void **)t.x, (void **)t.y, (void **)t.z, (void **)t.vx, (void **)t.vy, (void **)t.vz,
+                                 (void **)t.rest, (void **)t.flags, (void **)t.sync, (void **)t.pairs_all,
+                                 (void **)t.pair_counts, (void **)t.fx, (void **)t.fy, (void **)t.fz, (void **)t.mass,
+                                 (void **)t.radius, (void **)t.ff, (void **)t.fs, (void **)t.behavior};
     for (int q = 0; q < P && ok; ++q) {
         const PeerInfo &pi = info[(size_t)q];
-        for (int k = 0; k < 11 && ok; ++k) {
+        for (int k = 0; k < PEER_ARRAYS && ok; ++k) {
             void *ptr = nullptr;
             if (q == h->rank) {
                 ptr = mine[k];
@@ -940,8 +1079,10 @@ static int setup_peer_push(nb_handle h)
     for (int q = 0; q < P; ++q) ok = ok && info[(size_t)q].ok;
     cudaFree(d_info);
     if (!ok) {
+        // not an error (the NCCL all-gathers give the same bits), but never silent: nb_comm_mode reports 2
         h->peer_push = false;
         h->err = "peer-memory exchange unavailable (IPC / peer access failed); using NCCL all-gather";
+        std::fprintf(stderr, "[WARN] libnbody_b200 rank %d: %s\n", h->rank, h->err.c_str());
         return NB_OK;
     }
     NB_CUDA(h, cudaMalloc((void **)&h->d_peers, sizeof(PeerTable)));
@@ -978,6 +1119,13 @@ extern "C" int nb_comm_init(nb_handle h, int rank, int nranks, const void *id128
             h->pairs_all_base = h->d.pairs_all;
         }
     }
+    return NB_OK;
+}
+
+extern "C" int nb_comm_mode(nb_handle h, int *mode)
+{
+    if (!h || !mode) return NB_ERR_INVALID;
+    *mode = h->nranks <= 1 ? NB_COMM_SINGLE : (h->peer_push ? NB_COMM_PEER_PUSH : NB_COMM_NCCL);
     return NB_OK;
 }
 

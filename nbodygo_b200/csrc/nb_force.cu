@@ -151,6 +151,7 @@ __global__ void __launch_bounds__(TJ) k_prep(StepParams p)
     if (blockIdx.x == 0 && threadIdx.x < sizeof(Counters) / sizeof(unsigned))
         reinterpret_cast<unsigned *>(p.s.ctr)[threadIdx.x] = 0u;
     double r = 0.0, x = 1e150, y = 1e150, z = 1e150, m = 0.0;
+    bool live = false, dead_here = false;
     if (j < p.n) {
         const unsigned fl = p.s.flags[j];
         // calcForceFrom multiplies by the mass the body has during Compute; a subsume handled in
@@ -163,7 +164,12 @@ __global__ void __launch_bounds__(TJ) k_prep(StepParams p)
         // a live body at a non-finite (or absurd, |coord| >= 1e150: d2 would overflow) position is
         // inert as a j-body (the reference would poison every force with NaN); as an i-body it still
         // receives NaN and is culled by K4
-        const bool live = (fl & NB_F_EXISTS) != 0 && fabs(px) < 1e150 && fabs(py) < 1e150 && fabs(pz) < 1e150;
+        const bool finite = fabs(px) < 1e150 && fabs(py) < 1e150 && fabs(pz) < 1e150;
+        live = (fl & NB_F_EXISTS) != 0 && finite;
+        // a body that does not exist but is still in the array (SetNotExists at the cycle top, removed by
+        // the next Cycle) is skipped by the force sweep yet visited by the collision sweep
+        // (body.go:172-186 has no Exists filter): K1 looks at those few bodies separately (dead_j_sweep)
+        dead_here = !(fl & NB_F_EXISTS) && finite;
         if (live) {
             x = px; y = py; z = pz;
             r = p.s.radius[j];
@@ -175,12 +181,16 @@ __global__ void __launch_bounds__(TJ) k_prep(StepParams p)
     p.s.jy[j] = y;
     p.s.jz[j] = z;
     p.s.jm[j] = m;
-    // block max of r (NaN radii are ignored by fmax); block min / max of the effective mass
+    // block max of r (NaN radii are ignored by fmax); block min / max of the live masses
     __shared__ double red[TJ / 32], red_lo[TJ / 32], red_hi[TJ / 32];
-    // a tile is "uniform" if every one of its TJ slots holds a live body with the same positive finite
-    // mass (the tail of the last tile, dead and fragmenting bodies have m = 0 and break it)
-    const int odd = __syncthreads_or(!(m > 0.0 && m < INFINITY));
-    double mlo = m, mhi = m;
+    // A tile is "uniform" if every LIVE body in it has the same positive finite mass.  Slots without a
+    // live body (bodies that do not exist, the tail of the last tile) are parked at 1e150 and add an
+    // exact 0 to the mass-free sums of K1's uniform pass (y0^3 underflows to 0), so they match any
+    // mass; a fragmenting body stays at its position with m = 0 (it is still a collision partner) and
+    // breaks uniformity.
+    const int odd = __syncthreads_or(live && !(m > 0.0 && m < INFINITY));
+    const int any_dead = __syncthreads_or(dead_here);
+    double mlo = live ? m : INFINITY, mhi = live ? m : 0.0;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         r = fmax(r, __shfl_xor_sync(0xffffffffu, r, o));
@@ -202,7 +212,13 @@ __global__ void __launch_bounds__(TJ) k_prep(StepParams p)
             hi = fmax(hi, red_hi[w]);
         }
         p.s.tile_rmax[blockIdx.x] = mx;
-        p.s.tile_muni[blockIdx.x] = (p.uniform_tiles && !odd && lo == hi) ? lo : 0.0;
+        double mu = 0.0;
+        if (p.uniform_tiles && !odd) {
+            if (lo == hi) mu = lo;            // every live body has this mass
+            else if (hi == 0.0) mu = 1.0;     // no live body at all: the tile's sums are exact zeros
+        }
+        p.s.tile_muni[blockIdx.x] = mu;
+        p.s.tile_dead[blockIdx.x] = any_dead ? 1 : 0;
     }
 }
 
@@ -277,6 +293,54 @@ __device__ __noinline__ double exact_pair(const StepParams &p, long long i, long
         if ((p.opts & NB_STEP_COLLISIONS) && (fj.flags & NB_F_EXISTS)) emit_event(p, i, j, dist, ri, rj, bi, fj.behavior);
     }
     return 0.0;
+}
+
+// The collision sweep of Body.Compute has no Exists filter (body.go:172-186): a body that was set not
+// to exist at the cycle top (RemoveBodies / mod-body exists=false, computation-runner.go:176-216) but is
+// still in the array until the next Cycle is visited as `otherBody`.  Collision events with such a body
+// are no-ops (ResolveCollision's Exists gate, body.go:249-251) and are not queued; subsume events are
+// NOT gated (ResolveSubsume, body.go:228-244): a dead body with the larger radius still swallows a live
+// one, a dead body inside a live subsumer adds its mass.  Those bodies are parked far away in the
+// j-stream, so the tiled sweep never sees them; K0 flags the tiles that hold one and the CTAs of chunk 0
+// walk the few flagged tiles here (rare, and a handful of bodies when it happens).  One warp per call;
+// the body's own facts are re-read from global memory so that the hot kernel's registers stay its own.
+__device__ __noinline__ void dead_j_sweep(const StepParams &p, long long ibase, int stride, int R)
+{
+    const int lane = threadIdx.x & 31;
+    int any = 0;
+    for (int t = lane; t < p.n_tiles; t += 32) any |= p.s.tile_dead[t];
+    if (!__any_sync(0xffffffffu, any)) return;
+    for (int r = 0; r < R; ++r) {
+        const long long i = ibase + (long long)r * stride + threadIdx.x;
+        unsigned fl = 0;
+        if (i < p.i1) fl = p.s.flags[i];
+        const bool alive = (fl & NB_F_EXISTS) && !(fl & NB_F_FRAGMENTING);  // body.go:149-155
+        const double xi = alive ? p.s.x[i] : 0.0, yi = alive ? p.s.y[i] : 0.0, zi = alive ? p.s.z[i] : 0.0;
+        const double ri = alive ? p.s.radius[i] : 0.0;
+        const unsigned bi = alive ? p.s.behavior[i] : 0u;
+        for (int t = 0; t < p.n_tiles; ++t) {
+            if (!p.s.tile_dead[t]) continue;  // warp-uniform
+            const long long j0 = (long long)t * p.tj;
+            for (int jj = 0; jj < p.tj && j0 + jj < p.n; ++jj) {
+                const long long j = j0 + jj;
+                if (p.s.flags[j] & NB_F_EXISTS) continue;  // warp-uniform
+                const double xj = p.s.x[j], yj = p.s.y[j], zj = p.s.z[j];
+                if (!(fabs(xj) < 1e150 && fabs(yj) < 1e150 && fabs(zj) < 1e150)) continue;
+                const double rj = p.s.radius[j];
+                const unsigned bj = p.s.behavior[j];
+                if (!alive || j == i) continue;
+                if (elastic_or_fragment(bi) && elastic_or_fragment(bj)) continue;  // a gated no-op in the reference
+                if (!(bi == NB_SUBSUME || bj == NB_SUBSUME)) continue;
+                // Collided, body.go:192-208 (unfused)
+                const double dx = __dsub_rn(xj, xi), dy = __dsub_rn(yj, yi), dz = __dsub_rn(zj, zi);
+                const double d2 = __dadd_rn(__dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy)), __dmul_rn(dz, dz));
+                const double dist = __dsqrt_rn(d2);
+                const double s = __dadd_rn(ri, rj);
+                if (dist > s) continue;
+                if (dist <= s) emit_event(p, i, j, dist, ri, rj, bi, bj);
+            }
+        }
+    }
 }
 
 // Conservative integer screen: a pair whose radii sum to sr can only overlap (or be degenerate) if
@@ -534,6 +598,8 @@ __global__ void __launch_bounds__(NT, MINB) k_force(const __grid_constant__ Step
             p.s.pz[o] = az[r];
         }
     }
+    // bodies that do not exist but are still in the array: collision sweep only (see dead_j_sweep)
+    if (chunk == 0 && (p.opts & NB_STEP_COLLISIONS)) dead_j_sweep(p, ibase, NT, R);
 }
 
 template <int R, int NT, int MINB, int UNR, bool SPLIT = false>

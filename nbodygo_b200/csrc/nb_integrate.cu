@@ -76,6 +76,16 @@ __global__ void __launch_bounds__(INT_THREADS) k_integrate(const __grid_constant
                 }
             }
         }
+        // A body that does not compute (or will not, from the next cycle on: K3 just set `fragmenting`)
+        // keeps being updated with this stored force (body.go:152-155).  Cycle may move the shard
+        // boundaries before then, so every replica gets it.
+        if (p.peers && apply && (!computes || (fl & NB_F_FRAGMENTING))) {
+            const PeerTable &pt = *p.peers;
+            for (int q = 0; q < p.nranks; ++q) {
+                if (q == p.rank) continue;
+                pt.fx[q][i] = fx; pt.fy[q][i] = fy; pt.fz[q][i] = fz;
+            }
+        }
         // NewRenderable
         const bool ex = (fl & NB_F_EXISTS) != 0;
         dead = ex ? 0 : 1;
@@ -159,6 +169,43 @@ int launch_peer_signal(const StepParams &p, int slot_base, cudaStream_t st)
 int launch_peer_wait(const StepParams &p, int slot_base, cudaStream_t st)
 {
     k_peer_wait<<<1, MAX_RANKS, 0, st>>>(p, slot_base);
+    return 1;
+}
+
+// Sharded upload: the rank's slice [i0,i1) of the freshly copied arrays goes straight into every
+// peer's replica (coalesced NVLink peer stores), so that each host link carries n/P bodies, not n.
+__global__ void __launch_bounds__(INT_THREADS) k_push_shard(const __grid_constant__ StepParams p, unsigned mask)
+{
+    const long long i = p.i0 + (long long)blockIdx.x * INT_THREADS + threadIdx.x;
+    if (i >= p.i1) return;
+    const DevState &s = p.s;
+    const PeerTable &pt = *p.peers;
+    double *const src[11] = {s.x, s.y, s.z, s.vx, s.vy, s.vz, s.mass, s.radius, s.rest, s.ff, s.fs};
+    double *const *const dst[11] = {pt.x, pt.y, pt.z, pt.vx, pt.vy, pt.vz, pt.mass, pt.radius, pt.rest, pt.ff, pt.fs};
+#pragma unroll
+    for (int k = 0; k < 11; ++k) {
+        if (!(mask & (1u << k))) continue;
+        const double v = src[k][i];
+        for (int q = 0; q < p.nranks; ++q)
+            if (q != p.rank) dst[k][q][i] = v;
+    }
+    if (mask & PUSH_BEHAVIOR) {
+        const uint8_t v = s.behavior[i];
+        for (int q = 0; q < p.nranks; ++q)
+            if (q != p.rank) pt.behavior[q][i] = v;
+    }
+    if (mask & PUSH_FLAGS) {
+        const uint8_t v = s.flags[i];
+        for (int q = 0; q < p.nranks; ++q)
+            if (q != p.rank) pt.flags[q][i] = v;
+    }
+}
+
+int launch_push_shard(const StepParams &p, unsigned mask, cudaStream_t st)
+{
+    const long long n_local = p.i1 - p.i0;
+    if (n_local <= 0 || !mask) return 0;
+    k_push_shard<<<(unsigned)((n_local + INT_THREADS - 1) / INT_THREADS), INT_THREADS, 0, st>>>(p, mask);
     return 1;
 }
 

@@ -7,7 +7,8 @@
 //   fp64 output      fx fy fz
 //   u8               behavior flags
 //   per-tile         tile_rmax[n_tiles]  (max radius of the live bodies of a j-tile)
-//                    tile_muni[n_tiles]  (the mass every body of the tile has, or 0 if they differ)
+//                    tile_muni[n_tiles]  (the mass every live body of the tile has, or 0 if they differ)
+//                    tile_dead[n_tiles]  (1 if a !Exists body still sits in the tile at a finite position)
 //   partial sums     px py pz [S][n_pad_local]  (one slot per j-chunk, summed in
 //                    ascending chunk order by the integrate kernel — the result
 //                    for body i never depends on the grid or the rank count)
@@ -71,7 +72,10 @@ struct DevState {
     double *fx, *fy, *fz;
     uint8_t *behavior, *flags;
     double *tile_rmax;
-    double *tile_muni;          // > 0: every j-body of the tile is live with exactly this mass; 0: mixed (K0)
+    double *tile_muni;          // > 0: every live j-body of the tile has exactly this mass (slots without a live
+                                // body match any mass); 0: mixed (K0)
+    uint8_t *tile_dead;         // 1: the tile holds a body that does not exist but still sits in the array at a
+                                // finite position (visited by the collision sweep only: dead_j_sweep in K1)
     double *px, *py, *pz;
     float *render;
     uint8_t *render_exists;
@@ -107,9 +111,23 @@ struct PeerTable {
     unsigned long long *sync[MAX_RANKS];
     int2 *pairs_all[MAX_RANKS];               // base of rank q's gathered pair buffer: [2 parities][nranks][seg_cap]
     unsigned long long *pair_counts[MAX_RANKS];  // base of rank q's counts: [2 parities][MAX_RANKS]
+    // Body.fx,fy,fz of the bodies that do not compute (fragmenting: Update keeps applying the force of
+    // their last Compute, body.go:152-155) — pushed by K4 so that a shard boundary moved by Cycle finds
+    // them on the new owner
+    double *fx[MAX_RANKS], *fy[MAX_RANKS], *fz[MAX_RANKS];
+    // the fields only a sharded upload writes (nb_upload_shard)
+    double *mass[MAX_RANKS], *radius[MAX_RANKS], *ff[MAX_RANKS], *fs[MAX_RANKS];
+    uint8_t *behavior[MAX_RANKS];
 };
+constexpr int PEER_ARRAYS = 19;  // mapped arrays per rank (see setup_peer_push)
+// flag slots of a rank's sync block; every slot holds the last id its writer published (monotonic)
 constexpr int PEER_SLOT_ARRIVED = 0, PEER_SLOT_DONE = MAX_RANKS, PEER_SLOT_PAIRS = 2 * MAX_RANKS;
-constexpr int PEER_SYNC_SLOTS = 3 * MAX_RANKS;
+constexpr int PEER_SLOT_UP_READY = 3 * MAX_RANKS, PEER_SLOT_UP_ARRIVED = 4 * MAX_RANKS;
+constexpr int PEER_SYNC_SLOTS = 5 * MAX_RANKS;
+
+// which arrays a sharded upload pushes to the peers (bit k = field k of write_range's order:
+// x y z vx vy vz mass radius rest ff fs, then behavior (11) and flags (12))
+constexpr unsigned PUSH_BEHAVIOR = 1u << 11, PUSH_FLAGS = 1u << 12;
 
 struct StepParams {
     DevState s;
@@ -142,6 +160,8 @@ int launch_peer_signal(const StepParams &p, int slot_base, cudaStream_t st);
 int launch_peer_wait(const StepParams &p, int slot_base, cudaStream_t st);
 // copies this rank's pair list and count into every rank's gathered buffer (this cycle's parity)
 int launch_push_pairs(const StepParams &p, cudaStream_t st);
+// stores the rank's own slice [i0,i1) of the arrays in `mask` into every peer's replica (nb_upload_shard)
+int launch_push_shard(const StepParams &p, unsigned mask, cudaStream_t st);
 // stable compaction of !Exists bodies; returns launches. d_map[k] = old index of new body k.
 int launch_compact_map(const DevState &s, long long n, long long *d_map, unsigned *d_block_sums,
                        long long *d_new_n, cudaStream_t st);

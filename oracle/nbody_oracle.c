@@ -90,9 +90,11 @@ static inline void collision_pair(const orc_bodies *bc, int64_t i, int64_t j, ui
     double dist;
     if (!body_collided(bc, i, j, &dist)) return;
     if (i == j && !(opts & ORC_OPT_SELF_PAIRS)) return;
-    if (!exists(bc, j) && !(opts & ORC_OPT_DEAD_J)) return;
+    const int dead_j = !exists(bc, j);
+    if (dead_j && !(opts & (ORC_OPT_DEAD_J | ORC_OPT_DEAD_J_SUBSUME))) return;
     uint8_t bi = bc->behavior[i], bj = bc->behavior[j];
     if (elastic_or_fragment(bi) && elastic_or_fragment(bj)) {
+        if (dead_j && !(opts & ORC_OPT_DEAD_J)) return; /* a no-op in ResolveCollision */
         sink_push(s, ORC_EV_COLLISION, i, j, dist);
     } else if (bi == ORC_SUBSUME || bj == ORC_SUBSUME) {
         if (bc->radius[i] > bc->radius[j] && dist <= bc->radius[i])

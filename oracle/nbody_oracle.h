@@ -75,6 +75,11 @@ typedef struct {
 #define ORC_OPT_SELF_PAIRS 0x1u   /* keep (i,i) events like the reference (F5)   */
 #define ORC_OPT_DEAD_J 0x2u       /* keep events whose j does not exist (A2)      */
 #define ORC_OPT_SINGLE_SWEEP 0x4u /* fuse force+collision sweep (timing variant)  */
+#define ORC_OPT_DEAD_J_SUBSUME 0x8u /* keep the SUBSUME events whose j does not exist: ResolveSubsume
+                                     * (body.go:228-244) has no Exists gate, so they change state; the
+                                     * collision events with a dead j stay dropped (ResolveCollision's gate,
+                                     * body.go:249-251, makes them no-ops).  This is the canonical stream the
+                                     * device emits. */
 
 /* Body.Compute for i in [i0,i1): force sweep then collision sweep
  * (cmd/body/body.go:148-187, 192-225).  Events are appended to ev (capacity

@@ -18,6 +18,10 @@ _LIB = None
 OPT_SELF_PAIRS = 0x1
 OPT_DEAD_J = 0x2
 OPT_SINGLE_SWEEP = 0x4
+OPT_DEAD_J_SUBSUME = 0x8
+# the canonical event stream: i != j; collision events need a live j (dead-j ones are
+# no-ops in ResolveCollision); subsume events do not (ResolveSubsume has no Exists gate)
+OPT_CANONICAL = OPT_DEAD_J_SUBSUME
 
 EV_COLLISION, EV_SUBSUME, EV_FRAGMENT = 0, 1, 2
 
@@ -127,7 +131,7 @@ class OracleSim:
         return s
 
     # ---- Body.Compute over a slice ------------------------------------
-    def compute(self, i0=0, i1=None, opts=0, workers=None, ev_cap=None):
+    def compute(self, i0=0, i1=None, opts=OPT_CANONICAL, workers=None, ev_cap=None):
         b = self.b
         i1 = b.n if i1 is None else i1
         cap = ev_cap if ev_cap is not None else max(4096, 64 * b.n)
@@ -206,13 +210,13 @@ class OracleSim:
         b.n = int(n_new)
         return keep
 
-    def step(self, time_scaling, R, opts=0, workers=None):
+    def step(self, time_scaling, R, opts=OPT_CANONICAL, workers=None):
         """compute → ProcessMods → Update (cmd/runner/computation-runner.go:297-320)."""
         self.compute(opts=opts, workers=workers)
         self.process_mods()
         self.update(time_scaling, R)
 
-    # canonical pair set the GPU path emits: collision events, i != j, both exist
+    # canonical pair set the GPU path emits: collision events, i != j, both exist (OPT_CANONICAL)
     def collision_pairs(self):
         ev = self.events
         m = ev["kind"] == EV_COLLISION

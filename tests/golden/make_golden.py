@@ -75,11 +75,15 @@ def compute(bodies, i, events):
             continue
         if not (dist <= b.radius + o.radius):
             continue
-        # canonical pair set: i != j and j exists
-        if j == i or not o.exists:
+        # canonical event stream: no self pair; a collision event needs a live j
+        # (ResolveCollision's Exists gate makes the dead-j ones no-ops); a subsume event does not
+        # (body.go:172-186 has no Exists filter and ResolveSubsume, :228-244, has no gate)
+        if j == i:
             continue
         ef = (ELASTIC, FRAGMENT)
         if b.behavior in ef and o.behavior in ef:
+            if not o.exists:
+                continue
             events.append(("collision", i, j, dist))
         elif b.behavior == SUBSUME or o.behavior == SUBSUME:
             if b.radius > o.radius and dist <= b.radius:
@@ -263,6 +267,19 @@ def scenes():
     bodies[7].mass = 0.0
     bodies[20] = Body(0, 0, 0, -3, -3, -5, 5e13, 9, SUBSUME)
     out.append(run_scene("dense_mixed_48", bodies, 1e-3, 0.9, steps=4))
+    # bodies removed at the cycle top (mod-body exists=false keeps the mass; RemoveBodies zeroes it) stay
+    # in the array until Cycle: the collision sweep still visits them and ResolveSubsume is not gated
+    # (body.go:172-186,228-244).  0: deleted Subsume body with the larger radius -> swallows live 1;
+    # 2: live subsumer, 3: deleted small elastic body inside it that kept its mass -> 2 gains it;
+    # 4: deleted elastic body overlapping live elastic 5 -> collision event is a no-op, not queued
+    dj = [Body(0, 0, 0, 0, 0, 0, 7e10, 5.0, SUBSUME), Body(1, 1, 0, 2, 0, 0, 1e10, 1.0),
+          Body(100, 0, 0, 0, 1, 0, 4e10, 6.0, SUBSUME), Body(101, 2, 0, 0, 0, 0, 3e10, 1.0),
+          Body(200, 0, 0, 0, 0, 1, 2e10, 2.0), Body(201, 0, 0, -1, 0, 0, 2e10, 2.0)]
+    dj[0].exists = False
+    dj[3].exists = False
+    dj[4].exists = False
+    dj[4].mass = 0.0
+    out.append(run_scene("dead_j_subsume", dj, 1e-3, 1.0, steps=2))
     # touching pair: dist == r1+r2 exactly (predicate edge: collision, no force)
     out.append(run_scene("touching_exact",
                          [Body(0, 0, 0, 0.5, 0, 0, 1e10, 1.5), Body(3, 0, 0, -0.5, 0, 0, 1e10, 1.5),

@@ -62,6 +62,7 @@ def test_cuda_arm_json_assembly_with_a_stub_device(monkeypatch, capsys):
 
     class StubResult:
         ms_total, ms_force, n_pairs, resolve_rounds = 2.0, 1.5, 7, 2
+        ms_exchange, ms_resolve, ms_integrate = 0.0, 0.2, 0.3
 
     class StubSim:
         created = 0
@@ -72,14 +73,17 @@ def test_cuda_arm_json_assembly_with_a_stub_device(monkeypatch, capsys):
             self.uniform = os.environ.get("NB_UNIFORM_TILES", "1")
 
         def upload(self, b): pass
-        def upload_raw(self, n, *a, **k): assert len(a) == 8 and all(len(x) == n for x in a)
+
+        def upload_shard(self, n, first, count, *a, **k):
+            assert (first, count) == (0, n) and len(a) == 8 and all(len(x) == n for x in a)
 
         def step(self, ts, R, opts=capi.STEP_DEFAULT):
             self._l += 5
             return StubResult()
 
-        def download_into(self, **out): assert set(out) == {"x", "y", "z", "vx", "vy", "vz"}
-        def render(self, xyz, ex): assert xyz.shape == (self.n, 3)
+        def download_range_into(self, first, count, **out): assert set(out) == {"x", "y", "z", "vx", "vy", "vz"}
+        def render_range(self, first, count, xyz, ex): assert xyz.shape == (count, 3)
+        def comm_mode(self): return capi.COMM_SINGLE
         def launch_count(self): return self._l
         def close(self): pass
 
@@ -94,18 +98,32 @@ def test_cuda_arm_json_assembly_with_a_stub_device(monkeypatch, capsys):
     monkeypatch.delenv("WORLD_SIZE", raising=False)
     monkeypatch.delenv("RANK", raising=False)
     args = types.SimpleNamespace(gpus=1, steps=2, warmup=1, impl="ours", config="C4", n=20000,
-                                 no_cpu_baseline=True, no_e2e=False, time_scaling=1e-9)
+                                 no_cpu_baseline=True, no_e2e=False, time_scaling=1e-9, no_extra_configs=False,
+                                 no_parity_check=False)
     bench.run_ours(args)
     lines = [l for l in capsys.readouterr().out.splitlines() if l.strip()]
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert (REQUIRED - {"impl"}) <= set(d)
-    assert {"roofline", "gpu_launches", "clocks", "steps_per_s"} <= set(d)
+    assert {"roofline", "gpu_launches", "clocks", "steps_per_s", "exchange", "ms_exchange", "parity_check", "configs",
+            "run_stats"} <= set(d)
     rf = d["roofline"]
-    assert {"bound", "achieved", "peak", "unit", "frac", "traffic", "general_pass", "k1_passes"} <= set(rf)
+    assert {"bound", "achieved", "peak", "unit", "frac", "traffic", "traffic_source", "general_pass", "k1_passes"} <= set(rf)
     assert rf["general_pass"]["ms_per_launch"] == 1.5 and "frac" in rf["general_pass"]
     assert "of" in rf["k1_passes"] and "chunks uniform" in rf["k1_passes"]
     assert d["e2e"]["h2d_bytes_per_step"] == 20000 * 66 and d["e2e"]["d2h_bytes_per_step"] == 20000 * 61
     assert d["gpu_launches"] == 10 and d["n_gpus"] == 1 and d["cpu_baseline"] is None
+    assert d["exchange"] == "single" and d["parity_check"] is None and d["configs"] == []   # --bodies: headline only
     assert StubSim.created == 2 and "NB_UNIFORM_TILES" not in os.environ   # the side measurement cleaned up
     assert np.isclose(d["value"], 20000 * 19999 * 2 / (2 * 2.0e-3))
+    # both arms describe the workload with the same `config` object
+    assert d["config"] == bench.workload_config("C4", 20000, 1, 1e-9)
+
+    # the default run also carries the other BASELINE configs (C2, C3, the C5 sweep) in `configs`
+    args.n, args.no_e2e = 0, True
+    bench.run_ours(args)
+    d = json.loads([l for l in capsys.readouterr().out.splitlines() if l.strip()][0])
+    names = [(c["config"], c["n_bodies"]) for c in d["configs"]]
+    assert ("C2", 10_000) in names and ("C3", 100_000) in names and ("C5 sweep: C4", 256_000) in names
+    assert all("error" not in c and c["value"] > 0 and 0 < c["roofline_frac"] for c in d["configs"])
+    assert d["roofline"]["traffic"] is None or "profiles/" in d["roofline"]["traffic_source"]

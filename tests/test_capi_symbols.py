@@ -19,7 +19,7 @@ def test_header_symbols_are_exported():
     assert declared == set(capi.SYMBOLS), declared ^ set(capi.SYMBOLS)
     for sym in declared:
         assert hasattr(L, sym), sym
-    assert L.nb_abi_version() == 2
+    assert L.nb_abi_version() == 3
 
 
 def test_sm100a_sass_and_tma_present():
@@ -56,14 +56,17 @@ def test_uniform_chunk_report_mirrors_the_device_rule():
     import numpy as np
     from nbodygo_b200 import capi, clouds
     from nbodygo_b200.bodies import F_EXISTS
+    from nbodygo_b200.bodies import F_FRAGMENTING
     b = clouds.config("C4")
-    assert capi.uniform_chunks(b)[:2] == (31, 32)          # the chunk with the tail tile stays general
-    b.flags[5] &= ~np.uint8(F_EXISTS)                      # a dead body: its chunk goes general too
-    assert capi.uniform_chunks(b)[:2] == (30, 32)
+    assert capi.uniform_chunks(b)[:2] == (32, 32)          # the padding of the tail tile matches any mass
+    b.flags[5] &= ~np.uint8(F_EXISTS)                      # ... and so does a body that does not exist
+    assert capi.uniform_chunks(b)[:2] == (32, 32)
+    b.flags[700_000] |= np.uint8(F_FRAGMENTING)            # a fragmenting body stays in place with mass 0
+    assert capi.uniform_chunks(b)[:2] == (31, 32)
     c2 = clouds.config("C2")                               # 10 k bodies, masses U[1e24, 1e25]: single launch
     assert capi.uniform_chunks(c2)[0] == 0
     c3 = clouds.config("C3")
     nu, nc, tu, nt = capi.uniform_chunks(c3)
-    assert nu == nc - 1 and tu == nt - 1                   # 100 k equal masses: all but the tail
+    assert nu == nc and tu == nt                           # 100 k equal masses: every chunk
     c3.mass[::256] *= 1.5
     assert capi.uniform_chunks(c3)[0] == 0 and capi.uniform_chunks(c3)[2] == 0

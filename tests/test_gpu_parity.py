@@ -222,6 +222,48 @@ def test_subsume_is_resolved_on_device_in_event_order(capi):
     sim.close()
 
 
+@pytest.mark.parametrize("n", [500, 20_000], ids=["small-tiles", "large-tiles"])
+def test_deleted_bodies_still_take_part_in_subsume_events(capi, n):
+    """Bodies set not to exist at the cycle top (RemoveBodies zeroes the mass, mod-body exists=false keeps it;
+    computation-runner.go:176-216, body.go:93-96,308-309) stay in the array until Cycle.  The force sweep skips
+    them, the collision sweep does not (body.go:172-186) and ResolveSubsume has no Exists gate (:228-244): a
+    deleted body with the larger radius still swallows a live one, a deleted body inside a live subsumer adds
+    the mass it kept.  Events, masses and Exists bit-exact against the oracle's canonical stream."""
+    from oracle.oracle import EV_SUBSUME, OPT_CANONICAL
+    rng = np.random.default_rng(41)
+    side = 60.0 * (n / 500) ** (1 / 3)
+    b = clouds.uniform_cube(n, side, 1.0, 1e12, vmax=100.0, seed=43)
+    b.radius[:] = rng.uniform(0.5, 7.0, n)
+    b.mass[:] = rng.uniform(1e11, 1e13, n)
+    b.behavior[rng.random(n) < 0.35] = SUBSUME
+    b.behavior[rng.random(n) < 0.05] = NONE
+    dead = rng.random(n) < 0.15
+    b.flags[dead] &= ~np.uint8(F_EXISTS)
+    b.mass[dead & (rng.random(n) < 0.5)] = 0.0        # SetNotExists; the others keep their mass (exists=false mod)
+    o = oracle_sim(b.copy())
+    sim = capi.Sim(n)
+    sim.upload(b)
+    o.compute(opts=OPT_CANONICAL)
+    ref = sorted((int(e["a"]), int(e["b"]), float(e["dist"])) for e in o.events if e["kind"] == EV_SUBSUME)
+    with_dead = [e for e in ref if dead[e[0]] or dead[e[1]]]
+    assert len(with_dead) > 10 and any(dead[a] for a, _, _ in with_dead) and any(dead[b_] for _, b_, _ in with_dead)
+    ref_pairs = o.collision_pairs()
+    before = o.b.exists.copy()
+    o.process_mods()
+    o.update(1e-4, 0.9)
+    res = sim.step(1e-4, 0.9)
+    hev = sim.host_events()
+    assert [(int(e["a"]), int(e["b"]), float(e["dist"])) for e in hev if e["kind"] == capi.EV_SUBSUME] == ref
+    assert np.array_equal(sim.pairs(), ref_pairs)     # no collision event names a deleted body
+    g = sim.download()
+    assert np.array_equal(g.mass, o.b.mass) and np.array_equal(g.exists, o.b.exists)
+    assert res.n_subsumed == int((before & ~o.b.exists).sum()) > 0
+    for f in ("x", "vx", "vz"):
+        a, r = getattr(g, f), getattr(o.b, f)
+        assert np.allclose(a, r, rtol=1e-10, atol=1e-10 * np.max(np.abs(r))), f
+    sim.close()
+
+
 def test_subsume_report_only_when_step_is_not_applied(capi):
     b = BodyArrays.from_fields([0, 1, 50], [0, 0, 0], [0, 0, 0], [0, 0, 0], [0, 0, 0], [0, 0, 0],
                                [5e10, 1e10, 1e10], [4.0, 1.0, 1.0])

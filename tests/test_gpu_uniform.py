@@ -67,9 +67,9 @@ def test_uniform_pass_agrees_with_general_pass_and_exact_sum(capi):
 
 
 def test_every_tile_its_own_mass_and_some_chunks_mixed(capi):
-    # tile t has mass (1 + t % 7) * 1e23: uniform tiles, different masses inside one chunk;
-    # a dead body (chunk 3), a fragmenting-free odd mass (chunk 10) and the tail tile (last chunk)
-    # make three chunks mixed
+    # tile t has mass (1 + t % 7) * 1e23: uniform tiles, different masses inside one chunk; an odd mass
+    # makes chunk 10 mixed; a dead body (chunk 3) and the padding of the tail tile (last chunk) are
+    # parked far away and match any mass, so their chunks stay on the uniform pass
     b = clouds.uniform_cube(N, 1500.0, 1.2, 1e24, vmax=1e8, seed=6)
     b.mass[:] = (1 + (np.arange(N) // 256) % 7) * 1e23
     dead = chunk_start(capi, 3) + 17

@@ -203,6 +203,11 @@ int nb_download_render(nb_handle h, float *xyz, uint8_t *exists);
 int nb_render_buffers(nb_handle h, float **xyz, uint8_t **exists);
 /* Force accumulated on each body in the last step (Body.fx,fy,fz). */
 int nb_get_forces(nb_handle h, double *fx, double *fy, double *fz);
+/* Overwrites Body.fx,fy,fz of bodies [first, first+count).  Only a body that does not compute
+ * (fragmenting, body.go:152-155) ever reads them back: Update keeps applying the force of its last
+ * Compute.  nb_upload starts every body at 0 (NewBody, body.go:73-75); a host that re-uploads a
+ * running collection restores the forces it read with nb_get_forces through this call. */
+int nb_set_forces(nb_handle h, int64_t first, int64_t count, const double *fx, const double *fy, const double *fz);
 /* Elastic collision events of the last step as ordered pairs, sorted by
  * (i asc, j asc) — the single-worker arrival order of the reference.
  * *n receives the total; at most cap are written. */

@@ -36,6 +36,7 @@ SYMBOLS = (
     "nb_get_forces", "nb_get_pairs", "nb_get_host_events", "nb_comm_unique_id", "nb_comm_init",
     "nb_shard_range", "nb_plan", "nb_measure_fp64_peak", "nb_launch_count",
     "nb_graph_stats", "nb_upload_shard", "nb_download_state_range", "nb_download_render_range", "nb_comm_mode",
+    "nb_set_forces",
 )
 
 
@@ -96,6 +97,7 @@ def load(path: str | None = None):
     L.nb_download_render.argtypes = [H, C.POINTER(C.c_float), _U8P]
     L.nb_render_buffers.argtypes = [H, C.POINTER(C.POINTER(C.c_float)), C.POINTER(_U8P)]
     L.nb_get_forces.argtypes = [H, _DP, _DP, _DP]
+    L.nb_set_forces.argtypes = [H, C.c_int64, C.c_int64, _DP, _DP, _DP]
     L.nb_get_pairs.argtypes = [H, _I32P, _I32P, C.c_int64, _I64P]
     L.nb_get_host_events.argtypes = [H, C.c_void_p, C.c_int64, _I64P]
     L.nb_comm_unique_id.argtypes = [C.c_void_p]
@@ -250,6 +252,10 @@ class Sim:
         fx, fy, fz = np.zeros(n), np.zeros(n), np.zeros(n)
         self._chk(self.L.nb_get_forces(self.h, _p(fx), _p(fy), _p(fz)))
         return fx, fy, fz
+
+    def set_forces(self, first, count, fx, fy, fz):
+        fx, fy, fz = _f64(fx), _f64(fy), _f64(fz)
+        self._chk(self.L.nb_set_forces(self.h, first, count, _p(fx), _p(fy), _p(fz)))
 
     def pairs(self) -> np.ndarray:
         n = C.c_int64(0)

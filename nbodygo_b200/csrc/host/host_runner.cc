@@ -10,13 +10,20 @@
 namespace nbodygo {
 
 // ---------------------------------------------------------------- GpuStepper
-GpuStepper::GpuStepper(int device, int64_t capacity) : cap_(capacity)
+GpuStepper::GpuStepper(int device, int64_t capacity) : device_(device) { recreate(capacity, 0); }
+
+void GpuStepper::recreate(int64_t capacity, int64_t pairCapacity)
 {
-    const int rc = nb_create(device, capacity, 0, &h_);
+    if (h_) { nb_destroy(h_); h_ = nullptr; }
+    const int rc = nb_create(device_, capacity, pairCapacity, &h_);
     if (rc != NB_OK) {
         // no CPU fallback by design: the caller must not silently continue on the host
         throw std::runtime_error(std::string("[ERROR] nb_create: ") + nb_last_error(nullptr));
     }
+    cap_ = capacity;
+    pairCap_ = pairCapacity > 0 ? pairCapacity : 4 * capacity + 65536;  // nb_create's default
+    n_ = 0;
+    dirty_ = true;
     // the per-cycle Renderable snapshot lands in pinned host memory as part of the cycle itself
     if (nb_render_buffers(h_, &pinXyz_, &pinExists_) != NB_OK) { pinXyz_ = nullptr; pinExists_ = nullptr; }
 }
@@ -48,7 +55,11 @@ void GpuStepper::upload(BodyCollection &bc)
 {
     auto &arr = bc.GetArray();
     const size_t n = arr.size();
-    if ((int64_t)n > cap_) throw std::runtime_error("[ERROR] body count exceeds the device capacity");
+    if ((int64_t)n > cap_) {  // the reference's array just grows (body_collection.go:273-291): so does the device image
+        std::fprintf(stderr, "[INFO] device capacity %lld -> %lld bodies\n", (long long)cap_, (long long)(2 * n + 4096));
+        recreate((int64_t)(2 * n + 4096), 0);
+        stats_.regrows++;
+    }
     grow(n);
     for (size_t i = 0; i < n; ++i) {
         const Body &b = *arr[i];
@@ -59,6 +70,16 @@ void GpuStepper::upload(BodyCollection &bc)
     const int rc = nb_upload(h_, (int64_t)n, x.data(), y.data(), z.data(), vx.data(), vy.data(), vz.data(),
                              mass.data(), radius.data(), rest.data(), ff.data(), fs.data(), beh.data(), flags.data());
     if (rc != NB_OK) std::fprintf(stderr, "[ERROR] nb_upload: %s\n", nb_last_error(h_));
+    // nb_upload starts every body at fx = fy = fz = 0; a fragmenting body keeps applying the force of its
+    // last Compute (body.go:152-155), which SyncToHost brought back into Body.fx,fy,fz
+    bool anyFrag = false;
+    for (size_t i = 0; i < n && !anyFrag; ++i) anyFrag = arr[i]->fragmenting;
+    if (rc == NB_OK && anyFrag) {
+        hfx.resize(n); hfy.resize(n); hfz.resize(n);
+        for (size_t i = 0; i < n; ++i) { hfx[i] = arr[i]->fx; hfy[i] = arr[i]->fy; hfz[i] = arr[i]->fz; }
+        if (nb_set_forces(h_, 0, (int64_t)n, hfx.data(), hfy.data(), hfz.data()) != NB_OK)
+            std::fprintf(stderr, "[ERROR] nb_set_forces: %s\n", nb_last_error(h_));
+    }
     n_ = (int64_t)n;
     dirty_ = false;
     hostStale_ = false;
@@ -75,11 +96,14 @@ void GpuStepper::SyncToHost(BodyCollection &bc)
     const int rc = nb_download_state(h_, x.data(), y.data(), z.data(), vx.data(), vy.data(), vz.data(), nullptr,
                                      nullptr, rest.data(), nullptr, flags.data());
     if (rc != NB_OK) { std::fprintf(stderr, "[ERROR] nb_download_state: %s\n", nb_last_error(h_)); return; }
+    hfx.resize(n); hfy.resize(n); hfz.resize(n);
+    const bool haveF = nb_get_forces(h_, hfx.data(), hfy.data(), hfz.data()) == NB_OK;
     for (size_t i = 0; i < n; ++i) {
         Body &b = *arr[i];
         b.X = x[i]; b.Y = y[i]; b.Z = z[i]; b.Vx = vx[i]; b.Vy = vy[i]; b.Vz = vz[i];
         b.r = rest[i];
         b.collided = false;
+        if (haveF) { b.fx = hfx[i]; b.fy = hfy[i]; b.fz = hfz[i]; }
     }
     hostStale_ = false;
     stats_.downloads++;
@@ -90,6 +114,26 @@ bool GpuStepper::Step(BodyCollection &bc, double timeScaling, double R, ResultQu
     auto &arr = bc.GetArray();
     // fragmenting bodies spawn their fragments on the host, as Body.Compute does (body.go:152-155)
     const bool inStep = !dirty_ && (int64_t)arr.size() == n_;
+    // fragment() copies the body's CURRENT velocity into its fragments (fragcalc.go:97) and the device owns
+    // the velocities between syncs: refresh the fragmenting bodies first (a few bodies: one small range
+    // read each; many: one full sync)
+    if (hostStale_ && inStep) {
+        std::vector<size_t> fr;
+        for (size_t i = 0; i < arr.size(); ++i)
+            if (arr[i]->Exists && arr[i]->fragmenting) fr.push_back(i);
+        if (fr.size() > 16) {
+            SyncToHost(bc);
+        } else {
+            for (size_t i : fr) {
+                double v[6];
+                if (nb_download_state_range(h_, (int64_t)i, 1, &v[0], &v[1], &v[2], &v[3], &v[4], &v[5], nullptr, nullptr,
+                                            nullptr, nullptr, nullptr) != NB_OK)
+                    continue;
+                Body &b = *arr[i];
+                b.X = v[0]; b.Y = v[1]; b.Z = v[2]; b.Vx = v[3]; b.Vy = v[4]; b.Vz = v[5];
+            }
+        }
+    }
     for (size_t i = 0; i < arr.size(); ++i) {
         Body &b = *arr[i];
         if (b.Exists && b.fragmenting) {
@@ -106,9 +150,23 @@ bool GpuStepper::Step(BodyCollection &bc, double timeScaling, double R, ResultQu
     if (dirty_ || (int64_t)arr.size() != n_) upload(bc);
     const size_t n = arr.size();
     nb_step_result res{};
-    const int rc = nb_step(h_, timeScaling, R, NB_STEP_DEFAULT, &res);
+    int rc = nb_step(h_, timeScaling, R, NB_STEP_DEFAULT, &res);
+    if (rc == NB_ERR_PAIR_OVERFLOW) {
+        // the step was NOT applied: the device still holds the state of the cycle top.  The reference has
+        // no event capacity (its list grows), so neither has the stepper: bring the state back, re-create
+        // the handle with a larger event list and run the cycle again.
+        std::fprintf(stderr, "[INFO] event capacity %lld exceeded: growing\n", (long long)pairCap_);
+        hostStale_ = true;
+        SyncToHost(bc);
+        const int64_t bigger = std::max<int64_t>(4 * pairCap_, 16 * (int64_t)n + 65536);
+        recreate(cap_, bigger);
+        stats_.regrows++;
+        upload(bc);
+        rc = nb_step(h_, timeScaling, R, NB_STEP_DEFAULT, &res);
+    }
     if (rc != NB_OK) {
         std::fprintf(stderr, "[ERROR] nb_step: %s\n", nb_last_error(h_));
+        stats_.failed++;
         return false;
     }
     stats_.last = res;
@@ -182,6 +240,13 @@ bool GpuStepper::Step(BodyCollection &bc, double timeScaling, double R, ResultQu
         rq.Add(r);
     }
     return true;
+}
+
+void GpuStepper::Reserve(BodyCollection &bc, int64_t count)
+{
+    if (count <= cap_) return;
+    SyncToHost(bc);  // while host and device indices still correspond
+    dirty_ = true;   // upload() re-creates the handle with room for the new count
 }
 
 // After BodyCollection.Cycle: keep the device array in step with the host array without a full
@@ -331,8 +396,14 @@ void ComputationRunner::runOneComputation()
     if (bc_->Count() == 0 && bc_->pendingAdds() == 0) {
         std::this_thread::sleep_for(std::chrono::milliseconds(5));  // no bodies (:313)
     }
-    stepper_->Step(*bc_, timeScaling_, R_, *rq);
+    if (!stepper_->Step(*bc_, timeScaling_, R_, *rq)) {
+        // a failed device step changed nothing: publish nothing and do not Cycle (the queue handed out by
+        // NewResultQueue is simply dropped); the error is on stderr and in stats().failed
+        std::this_thread::sleep_for(std::chrono::milliseconds(5));
+        return;
+    }
     rqh_->Add(rq);
+    stepper_->Reserve(*bc_, (int64_t)bc_->Count() + (int64_t)bc_->pendingAdds());
     const bool changed = bc_->Cycle(R_);
     stepper_->AfterCycle(*bc_, changed, bc_->Count(), R_);
     computations_++;

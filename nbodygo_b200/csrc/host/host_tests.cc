@@ -399,6 +399,40 @@ static void TestSubsumeAndFragmentLoop()
     while (rqh.Next().second) {}
 }
 
+// The reference's body array and event list simply grow (body_collection.go:82-88,273-291).  With a
+// device image sized for 8 bodies the same fragmentation run has to outgrow it: the stepper refreshes the
+// host bodies, re-creates the handle and goes on — same population as with a roomy handle, no failed step.
+static void TestCapacityGrows()
+{
+    auto run = [](int64_t capacity, uint64_t *regrows, std::vector<double> *xs) {
+        ResetIdGenerator();
+        std::vector<BodyPtr> bodies = {
+            NewBody(NextId(), 0, 0, 0, 0, 0, 0, 9e20, 100, Subsume, Red, 0, 0, false, "big", "", false),
+            NewBody(NextId(), 50, 0, 0, 0, 0, 0, 1e10, 5, Elastic, Blue, 0, 0, false, "eaten", "", false),
+            NewBody(NextId(), 1000, 0, 0, 1e9, 0, 0, 1e12, 10, Elastic, Green, 0, 0, false, "target", "", false),
+            NewBody(NextId(), 1015, 0, 0, -1e9, 2e8, 0, 1e12, 10, Fragment, Yellow, 0.01, 100, false, "impactor", "", false)};
+        BodyCollection bc(bodies);
+        ResultQueueHolder rqh(100);
+        ComputationRunner cr(1, 1e-12, false, &rqh, &bc, 0, capacity);
+        for (int k = 0; k < 5; ++k) cr.runOneComputation();
+        *regrows = cr.Stepper().stats().regrows;
+        CHECK(cr.Stepper().stats().failed == 0 && cr.Computations() == 5);
+        CHECK(cr.Stepper().Capacity() >= bc.Count());
+        while (rqh.Next().second) {}
+        for (auto &b : bc.GetArray()) xs->push_back(b->X);
+    };
+    uint64_t g_small = 0, g_big = 0;
+    std::vector<double> small, big;
+    run(8, &g_small, &small);
+    run(100000, &g_big, &big);
+    CHECK(g_small >= 1 && g_big == 0);
+    CHECK(small.size() == big.size() && small.size() > 300);
+    // the re-upload restores the forces of fragmenting bodies, so both runs end in the same state
+    bool same = small.size() == big.size();
+    for (size_t i = 0; same && i < small.size(); ++i) same = small[i] == big[i];
+    CHECK(same);
+}
+
 static void TestHeadlessRun()
 {
     ResetIdGenerator();
@@ -425,7 +459,7 @@ int main(int argc, char **argv)
     std::vector<T> gpu = {{"TestWpCompute", TestWpCompute}, {"TestRunnerSetters", TestRunnerSetters},
                           {"TestCollide", TestCollide}, {"TestControlWindow", TestControlWindow},
                           {"TestSubsumeAndFragmentLoop", TestSubsumeAndFragmentLoop},
-                          {"TestHeadlessRun", TestHeadlessRun}};
+                          {"TestCapacityGrows", TestCapacityGrows}, {"TestHeadlessRun", TestHeadlessRun}};
     std::vector<T> *sets[] = {&cpu, nullptr};
     if (mode == "gpu") sets[0] = &gpu;
     if (mode == "nodevice") sets[0] = &nodev;

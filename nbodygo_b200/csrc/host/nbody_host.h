@@ -184,7 +184,8 @@ private:
 // ---------------------------------------------------------------- GPU stepper (replaces WorkPool)
 struct StepStats {
     nb_step_result last{};
-    uint64_t steps = 0, uploads = 0, appends = 0, compacts = 0, downloads = 0, patches = 0, subsumes = 0;
+    uint64_t steps = 0, uploads = 0, appends = 0, compacts = 0, downloads = 0, patches = 0, subsumes = 0, regrows = 0,
+             failed = 0;
     double ms_device = 0;
 };
 
@@ -198,14 +199,22 @@ public:
     void MarkDirty() { dirty_ = true; }        // host bodies changed: re-upload before the next step
     void SyncToHost(BodyCollection &bc);       // device state → host bodies (GetBody, mods, end of run)
     void AfterCycle(BodyCollection &bc, bool arrayChanged, int64_t newCount, double R);
+    // The reference's array simply grows (body_collection.go:273-291).  Call before Cycle appends: when
+    // `count` bodies will not fit, the host bodies are refreshed from the device while indices still match,
+    // and the next step re-creates the handle with room to spare and re-uploads.
+    void Reserve(BodyCollection &bc, int64_t count);
+    int64_t Capacity() const { return cap_; }
     const StepStats &stats() const { return stats_; }
     nb_handle handle() { return h_; }
 
 private:
     void upload(BodyCollection &bc);
     void grow(size_t n);
+    void recreate(int64_t capacity, int64_t pairCapacity);  // throws on failure, like the constructor
     nb_handle h_ = nullptr;
-    int64_t n_ = 0, cap_ = 0;
+    int device_ = 0;
+    int64_t n_ = 0, cap_ = 0, pairCap_ = 0;
+    std::vector<double> hfx, hfy, hfz;
     bool dirty_ = true, hostStale_ = false;
     std::vector<double> x, y, z, vx, vy, vz, mass, radius, rest, ff, fs;
     std::vector<uint8_t> beh, flags, exists;

@@ -921,6 +921,20 @@ extern "C" int nb_get_forces(nb_handle h, double *fx, double *fy, double *fz)
     return NB_OK;
 }
 
+extern "C" int nb_set_forces(nb_handle h, int64_t first, int64_t count, const double *fx, const double *fy,
+                             const double *fz)
+{
+    if (!h || first < 0 || count < 0 || first + count > h->n) return fail(h, NB_ERR_INVALID, "nb_set_forces: bad range");
+    NB_CUDA(h, cudaSetDevice(h->device));
+    const double *src[3] = {fx, fy, fz};
+    double *dst[3] = {h->d.fx, h->d.fy, h->d.fz};
+    for (int k = 0; k < 3; ++k)
+        if (src[k] && count > 0)
+            NB_CUDA(h, cudaMemcpyAsync(dst[k] + first, src[k], (size_t)count * sizeof(double), cudaMemcpyHostToDevice, h->st));
+    NB_CUDA(h, cudaStreamSynchronize(h->st));
+    return NB_OK;
+}
+
 extern "C" int nb_get_pairs(nb_handle h, int32_t *i, int32_t *j, int64_t cap, int64_t *n)
 {
     if (!h || !n) return NB_ERR_INVALID;

@@ -564,7 +564,12 @@ static void chunking(long long n, int &tj, int &n_tiles, int &n_chunks, int &til
     // enough chunks that the CTA grid has >= ~40 rounds per SM (tail < ~1 %), within [32, MAX_CHUNKS]
     long long want = n > 0 ? (CHUNK_TARGET_CTAS * 512 + n - 1) / n : 1;
     if (const char *e = getenv("NB_CHUNKS")) want = atoll(e);  // development override (tools/kbench.py)
-    int cap = (int)std::max<long long>(MIN_CHUNKS, std::min<long long>(want, MAX_CHUNKS));
+    // Large collections are the ones that get sharded over several GPUs: an eighth of 1 M bodies is 245
+    // i-blocks, and 245 x 32 CTAs are 26.5 waves over 296 resident slots — the half-empty last wave costs
+    // 2 % of K1 (measured at 8 GPUs).  Twice the slots halve the CTAs: at most one wave in 53 is partial, for
+    // 0.13 ms more K4 traffic at 1 M on one GPU.  (A function of n only, like the rest.)
+    const long long min_chunks = n >= LARGE_N_BELOW ? MAX_CHUNKS : MIN_CHUNKS;
+    int cap = (int)std::max<long long>(min_chunks, std::min<long long>(want, MAX_CHUNKS));
     int s = std::min(n_tiles, cap);
     if (s < 1) s = 1;
     tiles_per_chunk = (n_tiles + s - 1) / s;

@@ -113,29 +113,79 @@ __device__ __forceinline__ double rsqrt_seed_lo(double x, unsigned lo)
     return y;
 }
 
+// Compile-time experiment knobs for tools/k1_variants.py (the defaults are the production code):
+//   NB_EXP_KREG   1 (production): the constant 15/8 lives in a register pair built from an opaque zero, so ptxas
+//                 cannot rematerialise it with two IMAD.MOV per loop trip (uniform loop 274 -> 269 cycles per 8
+//                 pairs: one instruction less, and the yield hints fall off the accumulate triples)
+//   NB_EXP_POLY   1: w = s + s*(e*pp) instead of w = s*(1 + e*pp)
+//   NB_EXP_ACC    accumulate order inside a (body, j-pair) group: 0 = a.xyz then b.xyz, 1 = b then a,
+//                 2 = z y x, 3 = interleaved a.x b.x a.y b.y a.z b.z
+#ifndef NB_EXP_KREG
+#define NB_EXP_KREG 1
+#endif
+#ifndef NB_EXP_POLY
+#define NB_EXP_POLY 0
+#endif
+#ifndef NB_EXP_ACC
+#define NB_EXP_ACC 0
+#endif
+//   NB_EXP_LO     1: the running minimum of hi(d2) is updated after the accumulates (source order only)
+//   NB_EXP_PAD_GEN / NB_EXP_PAD_UNI   k: k extra one-cycle ALU instructions per loop trip of the per-body-mass /
+//                 uniform-mass loop (an opaque zero OR-ed into a dummy).  ptxas marks one instruction in every 12
+//                 issue cycles with a yield hint and never sets .reuse on it; when that instruction opens an
+//                 accumulate triple (w*dx, w*dy, w*dz share w through the reuse cache) the next one re-reads three
+//                 registers, +1 cycle.  One padding instruction moves the hints onto the third of each triple in
+//                 the per-body-mass loop (291 -> 287 cycles per 8 pairs by the issue model, tools/k1_variants.py);
+//                 the uniform loop is already in phase.
+//   NB_EXP_UNR4   unroll of the j-group loop of the production shape (R = 4)
+#ifndef NB_EXP_UNR4
+#define NB_EXP_UNR4 1
+#endif
+//   NB_EXP_LOOP   form of the j-group loop: 0 = index, 1 = pointer against its end, 2 = count down
+#ifndef NB_EXP_LOOP
+#define NB_EXP_LOOP 0
+#endif
+#ifndef NB_EXP_LO
+#define NB_EXP_LO 0
+#endif
+#ifndef NB_EXP_PAD_GEN
+#define NB_EXP_PAD_GEN 1
+#endif
+#ifndef NB_EXP_PAD_UNI
+#define NB_EXP_PAD_UNI 0
+#endif
+
 // w = mj * d2^(-3/2) from the seed y0: with e = 1 - d2*y0^2 (|e| <~ 2^-21),
 // d2^(-3/2) = y0^3 (1-e)^(-3/2) = y0^3 (1 + e(3/2 + 15/8 e) + O(e^3)).  7 FP64 ops, each reading at
 // most two distinct registers.
-__device__ __forceinline__ double w_from_seed(double y0, double d2, double mj)
+__device__ __forceinline__ double w_from_seed(double y0, double d2, double mj, double k1875 = 1.875)
 {
     const double u = __dmul_rn(y0, y0);
     const double e = __fma_rn(-d2, u, 1.0);
-    const double pp = __fma_rn(1.875, e, 1.5);
-    const double c = __fma_rn(e, pp, 1.0);
+    const double pp = __fma_rn(k1875, e, 1.5);
     const double t = __dmul_rn(mj, y0);
     const double tu = __dmul_rn(t, u);
+#if NB_EXP_POLY
+    return __fma_rn(tu, __dmul_rn(e, pp), tu);
+#else
+    const double c = __fma_rn(e, pp, 1.0);
     return __dmul_rn(tu, c);
+#endif
 }
 
 // The same without the mass: d2^(-3/2) (6 FP64 ops), for tiles whose bodies all have one mass.
-__device__ __forceinline__ double w_from_seed_uni(double y0, double d2)
+__device__ __forceinline__ double w_from_seed_uni(double y0, double d2, double k1875 = 1.875)
 {
     const double u = __dmul_rn(y0, y0);
     const double e = __fma_rn(-d2, u, 1.0);
-    const double pp = __fma_rn(1.875, e, 1.5);
-    const double c = __fma_rn(e, pp, 1.0);
+    const double pp = __fma_rn(k1875, e, 1.5);
     const double s = __dmul_rn(y0, u);
+#if NB_EXP_POLY
+    return __fma_rn(s, __dmul_rn(e, pp), s);
+#else
+    const double c = __fma_rn(e, pp, 1.0);
     return __dmul_rn(s, c);
+#endif
 }
 
 // ---------------------------------------------------------------- K0: prep
@@ -363,13 +413,39 @@ __device__ __forceinline__ void fast_tile(const double *sx, const double *sy, co
                                           const unsigned (&zlo)[2 * R], const int (&self_j)[R], double (&tx)[R],
                                           double (&ty)[R], double (&tz)[R], unsigned (&lo)[R])
 {
+#if NB_EXP_KREG
+    // 15/8 with an opaque (always zero) low word: a value, not a literal, so it stays in a register pair
+    const double k1875 = __hiloint2double(0x3ffe0000, (int)zlo[0]);
+#else
+    const double k1875 = 1.875;
+#endif
+    constexpr int PAD = UNI ? NB_EXP_PAD_UNI : NB_EXP_PAD_GEN;
+    unsigned pad = 0u;
+#if NB_EXP_LOOP == 1
+    // one induction variable: the smem byte offset, compared against its end
+#pragma unroll(UNR)
+    for (const double *pj = sx, *const pe = sx + TJ; pj != pe; pj += 2) {
+        const int jj = (int)(pj - sx);
+#define NB_LD(arr) (*reinterpret_cast<const double2 *>(pj + ((arr) - sx)))
+#elif NB_EXP_LOOP == 2
+    // count down to zero
+#pragma unroll(UNR)
+    for (int kk = TJ / 2; kk > 0; --kk) {
+        const int jj = TJ - 2 * kk;
+#define NB_LD(arr) (*reinterpret_cast<const double2 *>((arr) + jj))
+#else
 #pragma unroll(UNR)
     for (int jj = 0; jj < TJ; jj += 2) {
-        const double2 vx = *reinterpret_cast<const double2 *>(sx + jj);
-        const double2 vy = *reinterpret_cast<const double2 *>(sy + jj);
-        const double2 vz = *reinterpret_cast<const double2 *>(sz + jj);
+#define NB_LD(arr) (*reinterpret_cast<const double2 *>((arr) + jj))
+#endif
+#pragma unroll
+        for (int k = 0; k < PAD; ++k) asm volatile("or.b32 %0, %0, %1;" : "+r"(pad) : "r"(zlo[k % (2 * R)]));
+        const double2 vx = NB_LD(sx);
+        const double2 vy = NB_LD(sy);
+        const double2 vz = NB_LD(sz);
         double2 vm = make_double2(0.0, 0.0);
-        if (!UNI) vm = *reinterpret_cast<const double2 *>(sj + jj);
+        if (!UNI) vm = NB_LD(sj);
+#undef NB_LD
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const double dxa = __dsub_rn(vx.x, xi[r]), dxb = __dsub_rn(vx.y, xi[r]);
@@ -387,17 +463,46 @@ __device__ __forceinline__ void fast_tile(const double *sx, const double *sy, co
                 ya = __hiloint2double(sa ? 0 : __double2hiint(ya), __double2loint(ya));
                 yb = __hiloint2double(sb ? 0 : __double2hiint(yb), __double2loint(yb));
             }
+#if !NB_EXP_LO
             lo[r] = min(lo[r], min(ha, hb));
-            const double wa = UNI ? w_from_seed_uni(ya, d2a) : w_from_seed(ya, d2a, vm.x);
-            const double wb = UNI ? w_from_seed_uni(yb, d2b) : w_from_seed(yb, d2b, vm.y);
+#endif
+            const double wa = UNI ? w_from_seed_uni(ya, d2a, k1875) : w_from_seed(ya, d2a, vm.x, k1875);
+            const double wb = UNI ? w_from_seed_uni(yb, d2b, k1875) : w_from_seed(yb, d2b, vm.y, k1875);
+#if NB_EXP_ACC == 1
+            tx[r] = __fma_rn(wb, dxb, tx[r]);
+            ty[r] = __fma_rn(wb, dyb, ty[r]);
+            tz[r] = __fma_rn(wb, dzb, tz[r]);
+            tx[r] = __fma_rn(wa, dxa, tx[r]);
+            ty[r] = __fma_rn(wa, dya, ty[r]);
+            tz[r] = __fma_rn(wa, dza, tz[r]);
+#elif NB_EXP_ACC == 2
+            tz[r] = __fma_rn(wa, dza, tz[r]);
+            ty[r] = __fma_rn(wa, dya, ty[r]);
+            tx[r] = __fma_rn(wa, dxa, tx[r]);
+            tz[r] = __fma_rn(wb, dzb, tz[r]);
+            ty[r] = __fma_rn(wb, dyb, ty[r]);
+            tx[r] = __fma_rn(wb, dxb, tx[r]);
+#elif NB_EXP_ACC == 3
+            tx[r] = __fma_rn(wa, dxa, tx[r]);
+            tx[r] = __fma_rn(wb, dxb, tx[r]);
+            ty[r] = __fma_rn(wa, dya, ty[r]);
+            ty[r] = __fma_rn(wb, dyb, ty[r]);
+            tz[r] = __fma_rn(wa, dza, tz[r]);
+            tz[r] = __fma_rn(wb, dzb, tz[r]);
+#else
             tx[r] = __fma_rn(wa, dxa, tx[r]);
             ty[r] = __fma_rn(wa, dya, ty[r]);
             tz[r] = __fma_rn(wa, dza, tz[r]);
             tx[r] = __fma_rn(wb, dxb, tx[r]);
             ty[r] = __fma_rn(wb, dyb, ty[r]);
             tz[r] = __fma_rn(wb, dzb, tz[r]);
+#endif
+#if NB_EXP_LO
+            lo[r] = min(lo[r], min(ha, hb));
+#endif
         }
     }
+    if (PAD) lo[0] = min(lo[0], ~pad);  // pad stays 0
 }
 
 // ---------------------------------------------------------------- K1: kernel
@@ -640,7 +745,7 @@ int launch_force(const StepParams &p, cudaStream_t st, int force_R)
     // Values above 9 (NB_FORCE_R) select alternative launch shapes for tools/kbench.py:
     // 1000*UNR + 100*MINB + 10*(NT==256) + R.  Production shapes: R in {4,2,1}, NT 128.
     switch (R) {
-        case 4: return launch_force_t<4, 128, 1, 1, true>(p, st);
+        case 4: return launch_force_t<4, 128, 1, NB_EXP_UNR4, true>(p, st);
         case 2: return launch_force_t<2, 128, 1, 1, true>(p, st);
         case 1: return launch_force_t<1, 128, 1, 2, true>(p, st);
         case 3: return launch_force_t<3, 128, 1, 1>(p, st);

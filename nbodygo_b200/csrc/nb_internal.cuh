@@ -31,6 +31,7 @@ constexpr int NSTAGE = 2;    // smem stages of the j pipeline
 // j-chunks per body (= partial-sum slots; a function of n only, see chunking() in nb_api.cu)
 constexpr int MIN_CHUNKS = 32;
 constexpr int MAX_CHUNKS = 64;  // more slots cost K4 more than they gain K1 (tools/chunk_sweep.py: n = 32 k cycle 1114 -> 1092 us)
+constexpr long long LARGE_N_BELOW = 786432;  // n >= this always uses MAX_CHUNKS slots (multi-GPU wave tail, chunking())
 constexpr long long CHUNK_TARGET_CTAS = 148 * 2 * 40;  // (n/512) * chunks >= this when possible
 constexpr int MAX_RANKS = 16;
 // One event list for collisions and subsumes (event.go:20-24 kinds share one queue in the reference):

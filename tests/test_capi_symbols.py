@@ -58,11 +58,11 @@ def test_uniform_chunk_report_mirrors_the_device_rule():
     from nbodygo_b200.bodies import F_EXISTS
     from nbodygo_b200.bodies import F_FRAGMENTING
     b = clouds.config("C4")
-    assert capi.uniform_chunks(b)[:2] == (32, 32)          # the padding of the tail tile matches any mass
+    assert capi.uniform_chunks(b)[:2] == (64, 64)          # the padding of the tail tile matches any mass
     b.flags[5] &= ~np.uint8(F_EXISTS)                      # ... and so does a body that does not exist
-    assert capi.uniform_chunks(b)[:2] == (32, 32)
+    assert capi.uniform_chunks(b)[:2] == (64, 64)
     b.flags[700_000] |= np.uint8(F_FRAGMENTING)            # a fragmenting body stays in place with mass 0
-    assert capi.uniform_chunks(b)[:2] == (31, 32)
+    assert capi.uniform_chunks(b)[:2] == (63, 64)
     c2 = clouds.config("C2")                               # 10 k bodies, masses U[1e24, 1e25]: single launch
     assert capi.uniform_chunks(c2)[0] == 0
     c3 = clouds.config("C3")

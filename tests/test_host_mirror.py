@@ -34,7 +34,7 @@ def test_runner_refuses_to_start_without_device():
 def test_host_unit_tests_gpu():
     r = _run("gpu")
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
-    assert "6 tests, 0 failures" in r.stdout
+    assert "7 tests, 0 failures" in r.stdout
 
 
 @pytest.mark.gpu

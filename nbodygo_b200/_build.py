@@ -42,6 +42,35 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return SO
 
 
+def build_variant(name: str, force_flags: str) -> str:
+    """Development only (tools/k1_hw_variants.py): a copy of the library whose nb_force.cu is compiled with extra
+    -D knobs, as nbodygo_b200/variants/libnbody_b200_<name>.so.  The other translation units are compiled once."""
+    vdir = os.path.join(PKG, "variants")
+    os.makedirs(vdir, exist_ok=True)
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    base = [nvcc, *[f for f in NVCC_FLAGS if f != "-shared"], "-c"]
+    objs = []
+    for src in SOURCES:
+        if src == "nb_force.cu":
+            continue
+        obj = os.path.join(vdir, src.replace(".cu", ".o"))
+        if not os.path.exists(obj) or os.path.getmtime(obj) < max(
+                os.path.getmtime(os.path.join(CSRC, f)) for f in os.listdir(CSRC) if not os.path.isdir(os.path.join(CSRC, f))):
+            r = subprocess.run([*base, "-o", obj, os.path.join(CSRC, src)], capture_output=True, text=True)
+            if r.returncode != 0:
+                raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+        objs.append(obj)
+    fobj = os.path.join(vdir, f"nb_force_{name}.o")
+    r = subprocess.run([*base, *force_flags.split(), "-o", fobj, os.path.join(CSRC, "nb_force.cu")], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+    so = os.path.join(vdir, f"libnbody_b200_{name}.so")
+    r = subprocess.run([nvcc, "-shared", "-o", so, fobj, *objs, "-ldl"], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("link failed:\n" + r.stdout + r.stderr)
+    return so
+
+
 HOST_DIR = os.path.join(CSRC, "host")
 BIN_DIR = os.path.join(PKG, "bin")
 HOST_LIB_SOURCES = ("host_core.cc", "host_runner.cc", "host_sim.cc")

@@ -73,7 +73,8 @@ def load(path: str | None = None):
     global _LIB
     if _LIB is not None and path is None:
         return _LIB
-    so = path or _build.build()
+    # NB_LIBRARY_PATH: development override (tools/k1_hw_variants.py times alternative builds of the library)
+    so = path or os.environ.get("NB_LIBRARY_PATH") or _build.build()
     L = C.CDLL(so, mode=C.RTLD_GLOBAL)
     H = C.c_void_p
     state_in = [_DP] * 11 + [_U8P] * 2

@@ -115,13 +115,23 @@ __device__ __forceinline__ double rsqrt_seed_lo(double x, unsigned lo)
 
 // Compile-time experiment knobs for tools/k1_variants.py (the defaults are the production code):
 //   NB_EXP_KREG   1 (production): the constant 15/8 lives in a register pair built from an opaque zero, so ptxas
-//                 cannot rematerialise it with two IMAD.MOV per loop trip (uniform loop 274 -> 269 cycles per 8
-//                 pairs: one instruction less, and the yield hints fall off the accumulate triples)
+//                 cannot rematerialise it with two IMAD.MOV per loop trip: one instruction less per 8 pairs,
+//                 measured -0.55 % on the uniform-mass launch (60.03 -> 59.70 ms at n = 256 k)
 //   NB_EXP_POLY   1: w = s + s*(e*pp) instead of w = s*(1 + e*pp)
 //   NB_EXP_ACC    accumulate order inside a (body, j-pair) group: 0 = a.xyz then b.xyz, 1 = b then a,
 //                 2 = z y x, 3 = interleaved a.x b.x a.y b.y a.z b.z
 #ifndef NB_EXP_KREG
 #define NB_EXP_KREG 1
+#endif
+//   NB_EXP_KZ_GEN / NB_EXP_KZ_UNI   1: the constant gets an opaque zero of its own instead of sharing the first
+//                 seed's (one IMAD.MOV less per trip).  Measured at n = 256 k (profiles/r2_k1_variants.txt): the
+//                 per-body-mass loop gains 0.4 % with it, the uniform-mass loop LOSES 0.7 % — one instruction less,
+//                 slower: at this level the outcome is decided by how ptxas' schedule falls, not by counts.
+#ifndef NB_EXP_KZ_GEN
+#define NB_EXP_KZ_GEN 1
+#endif
+#ifndef NB_EXP_KZ_UNI
+#define NB_EXP_KZ_UNI 0
 #endif
 #ifndef NB_EXP_POLY
 #define NB_EXP_POLY 0
@@ -134,14 +144,15 @@ __device__ __forceinline__ double rsqrt_seed_lo(double x, unsigned lo)
 //                 uniform-mass loop (an opaque zero OR-ed into a dummy).  ptxas marks one instruction in every 12
 //                 issue cycles with a yield hint and never sets .reuse on it; when that instruction opens an
 //                 accumulate triple (w*dx, w*dy, w*dz share w through the reuse cache) the next one re-reads three
-//                 registers, +1 cycle.  One padding instruction moves the hints onto the third of each triple in
-//                 the per-body-mass loop (291 -> 287 cycles per 8 pairs by the issue model, tools/k1_variants.py);
-//                 the uniform loop is already in phase.
-//   NB_EXP_UNR4   unroll of the j-group loop of the production shape (R = 4)
+//                 registers.  By the round-1 issue model one padding instruction that moves the hints off the
+//                 triples should gain 1.4 % (291 -> 287 cycles per 8 pairs); MEASURED it loses 0.7 %
+//                 (tools/k1_hw_variants.py, profiles/r2_k1_variants.txt): in this loop a three-register read costs
+//                 nothing, every extra non-FP64 instruction costs ~1.5 cycles.  Kept as a knob, off.
+//   NB_EXP_UNR4   unroll of the j-group loop of the production shape (R = 4); 2 costs registers and MOVs
+//   NB_EXP_LOOP   form of the j-group loop: 0 = index, 1 = pointer against its end, 2 = count down (both worse)
 #ifndef NB_EXP_UNR4
 #define NB_EXP_UNR4 1
 #endif
-//   NB_EXP_LOOP   form of the j-group loop: 0 = index, 1 = pointer against its end, 2 = count down
 #ifndef NB_EXP_LOOP
 #define NB_EXP_LOOP 0
 #endif
@@ -149,7 +160,7 @@ __device__ __forceinline__ double rsqrt_seed_lo(double x, unsigned lo)
 #define NB_EXP_LO 0
 #endif
 #ifndef NB_EXP_PAD_GEN
-#define NB_EXP_PAD_GEN 1
+#define NB_EXP_PAD_GEN 0
 #endif
 #ifndef NB_EXP_PAD_UNI
 #define NB_EXP_PAD_UNI 0
@@ -410,12 +421,12 @@ __device__ __forceinline__ unsigned screen_threshold(double sr)
 template <int R, int UNR, bool SELF, bool UNI, int TJ>
 __device__ __forceinline__ void fast_tile(const double *sx, const double *sy, const double *sz, const double *sj,
                                           const double (&xi)[R], const double (&yi)[R], const double (&zi)[R],
-                                          const unsigned (&zlo)[2 * R], const int (&self_j)[R], double (&tx)[R],
+                                          const unsigned (&zlo)[2 * R + 1], const int (&self_j)[R], double (&tx)[R],
                                           double (&ty)[R], double (&tz)[R], unsigned (&lo)[R])
 {
 #if NB_EXP_KREG
     // 15/8 with an opaque (always zero) low word: a value, not a literal, so it stays in a register pair
-    const double k1875 = __hiloint2double(0x3ffe0000, (int)zlo[0]);
+    const double k1875 = __hiloint2double(0x3ffe0000, (int)zlo[(UNI ? NB_EXP_KZ_UNI : NB_EXP_KZ_GEN) ? 2 * R : 0]);
 #else
     const double k1875 = 1.875;
 #endif
@@ -557,9 +568,9 @@ __global__ void __launch_bounds__(NT, MINB) k_force(const __grid_constant__ Step
     double xi[R], yi[R], zi[R], ri[R];
     double ax[R], ay[R], az[R];
     bool alive[R];
-    unsigned zlo[2 * R];  // opaque zeros: low words of the rsqrt seeds (see rsqrt_seed_lo)
+    unsigned zlo[2 * R + 1];  // opaque zeros: low words of the rsqrt seeds (see rsqrt_seed_lo) and of the constant 15/8
 #pragma unroll
-    for (int k = 0; k < 2 * R; ++k) zlo[k] = __ldcg(&p.s.zeros[(tid + 32 * k) & 1023]);
+    for (int k = 0; k < 2 * R + 1; ++k) zlo[k] = __ldcg(&p.s.zeros[(tid + 32 * k) & 1023]);
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         const long long i = ibase + (long long)r * NT + tid;

@@ -36,21 +36,21 @@ def test_every_production_pass_has_its_two_fast_loops(loops):
 
 
 @pytest.mark.parametrize("mode,fp64,lds,max_instr,max_cycles", [
-    (0, 128, 4, 151, 287),    # per-body masses: 16 FP64 instructions per pair (+1 phase-padding instruction)
-    (1, 128, 4, 151, 287),
+    (0, 128, 4, 150, 290),    # per-body masses: 16 FP64 instructions per pair
+    (1, 128, 4, 150, 290),
     (2, 120, 3, 141, 269),    # uniform-mass pass: 15 per pair, no LDS of the masses
 ])
 def test_fast_loop_budget(loops, mode, fp64, lds, max_instr, max_cycles):
-    """Round 2: the constant 15/8 stays in a register pair (no IMAD.MOV pair per trip) and ptxas' periodic yield
-    hints fall on the third instruction of the accumulate triples, so only the 8 inherent first accumulates
-    read three registers (round 1: 12, and 291 / 274 cycles).  The issue model reproduced the measured launch
-    to 0.1 % (profiles/r2_summary.md), so a regression here is a regression of the headline."""
+    """Round 2: the constant 15/8 stays in a register pair (one IMAD.MOV less per trip; measured -0.55 % on the
+    uniform-mass launch).  What the hardware measurements of round 2 showed (profiles/r2_k1_variants.txt): the
+    instruction COUNT is what matters — every non-FP64 instruction costs about 1.5 issue cycles with two warps per
+    scheduler — while the three-register reads the round-1 model charged a cycle for are free here.  So the budget
+    pins counts; `cycles` (the round-1 model) is kept as a loose cap only."""
     L = loops[(mode, False)]
     h = L["hist"]
     assert L["fp64"] == fp64                      # 8 pairs per iteration
     assert h.get("MUFU") == 8 and h.get("LDS") == lds and h.get("VIMNMX3") == 4
     assert h.get("IMAD", 0) <= 1                  # no per-pair MOVs, no rematerialised constant
-    assert L["three"] == 8                        # one per pair: w, d and the accumulator are all fresh
     assert not any(k in h for k in ("LDL", "STL", "LDG", "CALL", "BAR", "SEL", "ISETP"))
     assert L["n"] <= max_instr and L["cycles"] <= max_cycles, (L["n"], L["cycles"])
 

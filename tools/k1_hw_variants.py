@@ -1,0 +1,81 @@
+#!/usr/bin/env python3
+"""Times K1 for alternative builds of nb_force.cu (-DNB_EXP_* knobs) on the GPU — the issue model of
+tools/sass_model.py ranks them offline, this measures them.
+
+  python tools/k1_hw_variants.py build          # here (no GPU): compiles nbodygo_b200/variants/*.so
+  python tools/k1_hw_variants.py run [--n 256000]      # on the GPU box: one subprocess per variant
+
+Each variant is timed on the C4 cloud with the uniform-mass pass (all chunks uniform) and with
+NB_UNIFORM_TILES=0 (per-body-mass pass); best of 4 launches each."""
+import json
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+VARIANTS = {
+    "r1": "-DNB_EXP_KREG=0",
+    "prod": "",
+    "kz": "-DNB_EXP_KZ=1",
+    "kz_acc3": "-DNB_EXP_KZ=1 -DNB_EXP_ACC=3",
+    "kz_poly": "-DNB_EXP_KZ=1 -DNB_EXP_POLY=1",
+    "kz_lo": "-DNB_EXP_KZ=1 -DNB_EXP_LO=1",
+    "kz_unr2": "-DNB_EXP_KZ=1 -DNB_EXP_UNR4=2",
+    "unr2": "-DNB_EXP_UNR4=2",
+}
+
+
+def child(n):
+    from nbodygo_b200 import capi, clouds
+    b = clouds.config("C4", n=n)
+    out = {}
+    for uni in (1, 0):
+        os.environ["NB_UNIFORM_TILES"] = str(uni)
+        sim = capi.Sim(b.n)
+        sim.upload(b)
+        o = capi.STEP_COLLISIONS | capi.STEP_NO_INTEGRATE | capi.STEP_PHASE_TIMINGS
+        sim.step(1e-9, 1.0, o)
+        out["uni" if uni else "gen"] = min(sim.step(1e-9, 1.0, o).ms_force for _ in range(4))
+        sim.close()
+    print(json.dumps(out))
+
+
+def main():
+    mode = sys.argv[1] if len(sys.argv) > 1 else "run"
+    n = int(sys.argv[sys.argv.index("--n") + 1]) if "--n" in sys.argv else 256_000
+    if mode == "child":
+        return child(n)
+    from nbodygo_b200 import _build
+    if mode == "build":
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import sass_model
+        for name, flags in VARIANTS.items():
+            so = _build.build_variant(name, flags)
+            unr = "2" if "UNR4=2" in flags else "1"
+            rows = {r[0].split("ELi256ELi")[1][0]: (r[6], r[2], r[2] - r[4])
+                    for r in sass_model.hot_loops(so, f"k_forceILi4ELi128ELi1ELi{unr}ELi256") if not r[3].get("SEL", 0)}
+            print(f"{name:14s} {flags:60s} (model cycles, instr, non-FP64): uniform {rows.get('2')} general {rows.get('1')}", flush=True)
+        return
+    vdir = os.path.join(ROOT, "nbodygo_b200", "variants")
+    base = None
+    for name in VARIANTS:
+        so = os.path.join(vdir, f"libnbody_b200_{name}.so")
+        if not os.path.exists(so):
+            continue
+        env = dict(os.environ, NB_LIBRARY_PATH=so)
+        r = subprocess.run([sys.executable, os.path.abspath(__file__), "child", "--n", str(n)], env=env,
+                           capture_output=True, text=True)
+        try:
+            t = json.loads(r.stdout.strip().splitlines()[-1])
+        except Exception:  # noqa: BLE001
+            print(name, "failed:", r.stderr[-300:])
+            continue
+        base = base or t
+        print(f"{name:14s} uniform {t['uni']:9.3f} ms ({100 * (t['uni'] / base['uni'] - 1):+5.2f} %)   "
+              f"general {t['gen']:9.3f} ms ({100 * (t['gen'] / base['gen'] - 1):+5.2f} %)", flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -93,6 +93,13 @@ typedef struct {
 #define NB_EV_COLLISION 0 /* reserved                                               */
 #define NB_EV_SUBSUME 1   /* a subsumed b (larger radius first), body.go:178-184,228-244 */
 #define NB_EV_FRAGMENT 2  /* shouldFragment said yes: f1/f2 = thisFactor/otherFactor */
+#define NB_EV_FRAG_INIT 3 /* initiateFragmentation ran for body a (partner b) while the queue was processed
+                           * (fragcalc.go:54-83): dist = a's Mass AT THAT POINT of the queue (earlier subsumes
+                           * included, later ones not), f1 = the fragFactor it was called with, applied = 1 if a
+                           * is the event's b1, 2 if it is b2.  One record per call, reported in the reference's
+                           * handling order, so that a host replays them in sequence (a body named twice keeps the
+                           * fragInfo of the later call, as in the reference).  The position the reference records
+                           * (fragcalc.go:77) is the one before Update: nb_get_cycle_top_positions. */
 
 typedef struct {
     int32_t kind;
@@ -212,7 +219,11 @@ int nb_set_forces(nb_handle h, int64_t first, int64_t count, const double *fx, c
  * (i asc, j asc) — the single-worker arrival order of the reference.
  * *n receives the total; at most cap are written. */
 int nb_get_pairs(nb_handle h, int32_t *i, int32_t *j, int64_t cap, int64_t *n);
-/* Subsume / fragment records of the last step, sorted by (kind, a, b).  (With
+/* Positions the last nb_step started from — what Body.X,Y,Z held while ProcessMods ran (Update moves them
+ * afterwards).  Valid for bodies that existed at finite positions at the top of that cycle, until the next step.
+ * The host-only half of initiateFragmentation (fragInfo.curPos, fragcalc.go:77) reads them. */
+int nb_get_cycle_top_positions(nb_handle h, int64_t first, int64_t count, double *x, double *y, double *z);
+/* Subsume / fragment records of the last step, sorted by (kind, a, b); NB_EV_FRAG_INIT records in handling order.  (With
  * NB_STEP_NO_RESOLVE the unresolved collision events are the pair list of
  * nb_get_pairs.)  On several GPUs the subsume records cover the handle's own
  * i-range — merge the handles' lists — while the fragment records come from the

@@ -36,6 +36,17 @@ func (b *Body) DoFragment(otherBody *Body, thisFactor, otherFactor float64) {
 	b.doFragment(otherBody, thisFactor, otherFactor)
 }
 
+// InitiateFragmentationAt runs initiateFragmentation (fragcalc.go:66-83) on the Mass and position the body had
+// when its event was handled.  On the GPU path the device resolves the whole event queue; an NB_EV_FRAG_INIT
+// record carries the mass of that moment (after the subsumes handled earlier in the queue), and
+// nb_get_cycle_top_positions the position before Update.  The reference's own routine does the bookkeeping.
+func (b *Body) InitiateFragmentationAt(fragFactor, massThen, x, y, z float64) {
+	m, px, py, pz := b.Mass, b.X, b.Y, b.Z
+	b.Mass, b.X, b.Y, b.Z = massThen, x, y, z
+	b.initiateFragmentation(fragFactor)
+	b.Mass, b.X, b.Y, b.Z = m, px, py, pz
+}
+
 // Fragment runs fragment (fragcalc.go:90-117): spawns the next batch of fragments as add events.
 func (b *Body) Fragment(bc *BodyCollection) { b.fragment(bc) }
 

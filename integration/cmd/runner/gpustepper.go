@@ -278,19 +278,26 @@ func (g *GpuStepper) Step(bc *body.BodyCollection, timeScaling, R float64, rq *R
 		ev := make([]C.nb_event, int(res.n_host_events))
 		var m C.int64_t
 		C.nb_get_host_events(g.h, &ev[0], C.int64_t(len(ev)), &m)
-		anyFragment, anySubsume := false, false
+		nFragInit, anySubsume := 0, false
 		for _, e := range ev[:int(m)] {
-			anyFragment = anyFragment || e.kind == C.NB_EV_FRAGMENT
+			if e.kind == C.NB_EV_FRAG_INIT {
+				nFragInit++
+			}
 			anySubsume = anySubsume || (e.kind == C.NB_EV_SUBSUME && e.applied != 0)
-		}
-		if anyFragment {
-			g.SyncToHost(bc) // initiateFragmentation records the body's position (fragcalc.go:81)
-			g.hostStale = true
 		}
 		if anySubsume {
 			if rc := C.nb_download_state(g.h, nil, nil, nil, nil, nil, nil, dptr(g.mass), nil, nil, nil,
 				bptr(g.flags)); rc != C.NB_OK {
 				log.Printf("[ERROR] nb_download_state: %s", g.lastError())
+				return false
+			}
+		}
+		// initiateFragmentation records where the body was while the queue was processed (fragcalc.go:77): the
+		// position the cycle started from, not the one Update produced.  Many records: one bulk read.
+		bulkPos := nFragInit > 16
+		if bulkPos {
+			if rc := C.nb_get_cycle_top_positions(g.h, 0, C.int64_t(n), dptr(g.x), dptr(g.y), dptr(g.z)); rc != C.NB_OK {
+				log.Printf("[ERROR] nb_get_cycle_top_positions: %s", g.lastError())
 				return false
 			}
 		}
@@ -312,8 +319,15 @@ func (g *GpuStepper) Step(bc *body.BodyCollection, timeScaling, R float64, rq *R
 				if g.flags[b]&C.NB_F_EXISTS == 0 {
 					arr[b].Exists = false
 				}
-			case e.kind == C.NB_EV_FRAGMENT:
-				arr[a].DoFragment(arr[b], float64(e.f1), float64(e.f2)) // fragcalc.go:54-61
+			case e.kind == C.NB_EV_FRAG_INIT:
+				// in the reference's handling order (the library sorts them): a body named twice keeps the later call
+				var px, py, pz C.double
+				if bulkPos {
+					px, py, pz = C.double(g.x[a]), C.double(g.y[a]), C.double(g.z[a])
+				} else if rc := C.nb_get_cycle_top_positions(g.h, C.int64_t(a), 1, &px, &py, &pz); rc != C.NB_OK {
+					continue
+				}
+				arr[a].InitiateFragmentationAt(float64(e.f1), float64(e.dist), float64(px), float64(py), float64(pz))
 			}
 		}
 	}

@@ -24,7 +24,7 @@ STEP_ASYNC = 0x08
 STEP_PHASE_TIMINGS = 0x10   # ms_prep .. ms_integrate (costs a few us of a small cycle)
 STEP_DEFAULT = STEP_COLLISIONS
 
-EV_COLLISION, EV_SUBSUME, EV_FRAGMENT = 0, 1, 2
+EV_COLLISION, EV_SUBSUME, EV_FRAGMENT, EV_FRAG_INIT = 0, 1, 2, 3
 
 COMM_SINGLE, COMM_PEER_PUSH, COMM_NCCL = 0, 1, 2
 COMM_MODE_NAMES = {COMM_SINGLE: "single", COMM_PEER_PUSH: "peer_push", COMM_NCCL: "nccl"}
@@ -36,7 +36,7 @@ SYMBOLS = (
     "nb_get_forces", "nb_get_pairs", "nb_get_host_events", "nb_comm_unique_id", "nb_comm_init",
     "nb_shard_range", "nb_plan", "nb_measure_fp64_peak", "nb_launch_count",
     "nb_graph_stats", "nb_upload_shard", "nb_download_state_range", "nb_download_render_range", "nb_comm_mode",
-    "nb_set_forces",
+    "nb_set_forces", "nb_get_cycle_top_positions",
 )
 
 
@@ -99,6 +99,7 @@ def load(path: str | None = None):
     L.nb_render_buffers.argtypes = [H, C.POINTER(C.POINTER(C.c_float)), C.POINTER(_U8P)]
     L.nb_get_forces.argtypes = [H, _DP, _DP, _DP]
     L.nb_set_forces.argtypes = [H, C.c_int64, C.c_int64, _DP, _DP, _DP]
+    L.nb_get_cycle_top_positions.argtypes = [H, C.c_int64, C.c_int64, _DP, _DP, _DP]
     L.nb_get_pairs.argtypes = [H, _I32P, _I32P, C.c_int64, _I64P]
     L.nb_get_host_events.argtypes = [H, C.c_void_p, C.c_int64, _I64P]
     L.nb_comm_unique_id.argtypes = [C.c_void_p]
@@ -253,6 +254,12 @@ class Sim:
         fx, fy, fz = np.zeros(n), np.zeros(n), np.zeros(n)
         self._chk(self.L.nb_get_forces(self.h, _p(fx), _p(fy), _p(fz)))
         return fx, fy, fz
+
+    def cycle_top_positions(self, first, count):
+        """(x, y, z) the last step started from, for bodies [first, first+count)."""
+        x, y, z = np.zeros(count), np.zeros(count), np.zeros(count)
+        self._chk(self.L.nb_get_cycle_top_positions(self.h, first, count, _p(x), _p(y), _p(z)))
+        return x, y, z
 
     def set_forces(self, first, count, fx, fy, fz):
         fx, fy, fz = _f64(fx), _f64(fy), _f64(fz)

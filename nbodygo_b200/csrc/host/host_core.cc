@@ -140,6 +140,15 @@ void Body::initiateFragmentation(double fragFactor)
     fragInfo = FragInfo{Radius, newRadius, newMass, (int)fragments, X, Y, Z};
 }
 
+void Body::initiateFragmentationAt(double fragFactor, double massThen, double x, double y, double z)
+{
+    // run the reference's own routine on the state of that moment, then put the current state back
+    const double m = Mass, px = X, py = Y, pz = Z;
+    Mass = massThen; X = x; Y = y; Z = z;
+    initiateFragmentation(fragFactor);
+    Mass = m; X = px; Y = py; Z = pz;
+}
+
 // util.GetVectorEven (cmd/util/vectorutil.go:32-42), seeded per body instead of from the clock
 static void vectorEven(std::mt19937_64 &rng, double cx, double cy, double cz, double radius, double out[3])
 {

@@ -182,16 +182,23 @@ bool GpuStepper::Step(BodyCollection &bc, double timeScaling, double R, ResultQu
         std::vector<nb_event> ev((size_t)res.n_host_events);
         int64_t m = 0;
         nb_get_host_events(h_, ev.data(), (int64_t)ev.size(), &m);
-        bool anyFragment = false, anySubsume = false;
+        int nFragInit = 0;
+        bool anySubsume = false;
         for (int64_t k = 0; k < m; ++k) {
-            anyFragment |= ev[(size_t)k].kind == NB_EV_FRAGMENT;
+            nFragInit += ev[(size_t)k].kind == NB_EV_FRAG_INIT;
             anySubsume |= ev[(size_t)k].kind == NB_EV_SUBSUME && ev[(size_t)k].applied;
         }
-        if (anyFragment) SyncToHost(bc);  // initiateFragmentation records the body's current position
         if (anySubsume &&
             nb_download_state(h_, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, mass.data(), nullptr, nullptr,
                               nullptr, flags.data()) != NB_OK) {
             std::fprintf(stderr, "[ERROR] nb_download_state: %s\n", nb_last_error(h_));
+            return false;
+        }
+        // initiateFragmentation records where the body was while the queue was processed (fragcalc.go:77): the
+        // position the cycle started from, not the one Update produced.  Many records: one bulk read.
+        const bool bulkPos = nFragInit > 16;
+        if (bulkPos && nb_get_cycle_top_positions(h_, 0, (int64_t)n, x.data(), y.data(), z.data()) != NB_OK) {
+            std::fprintf(stderr, "[ERROR] nb_get_cycle_top_positions: %s\n", nb_last_error(h_));
             return false;
         }
         for (int64_t k = 0; k < m; ++k) {
@@ -206,11 +213,13 @@ bool GpuStepper::Step(BodyCollection &bc, double timeScaling, double R, ResultQu
                 if (!(flags[(size_t)e.a] & NB_F_EXISTS)) a.Exists = false;
                 if (!(flags[(size_t)e.b] & NB_F_EXISTS)) b.Exists = false;
                 stats_.subsumes++;
-            } else if (e.kind == NB_EV_FRAGMENT) {
-                bc.Enqueue(newFragment(arr[(size_t)e.a], arr[(size_t)e.b], e.f1, e.f2));
+            } else if (e.kind == NB_EV_FRAG_INIT) {
+                // in the reference's handling order (the library sorts them): a body named twice keeps the later call
+                double p[3] = {x[(size_t)e.a], y[(size_t)e.a], z[(size_t)e.a]};
+                if (!bulkPos && nb_get_cycle_top_positions(h_, e.a, 1, &p[0], &p[1], &p[2]) != NB_OK) continue;
+                arr[(size_t)e.a]->initiateFragmentationAt(e.f1, e.dist, p[0], p[1], p[2]);
             }
         }
-        if (anyFragment) bc.ProcessMods();
     }
     // Renderables from the float32 snapshot (13 B/body) — computation-runner.go:317-320
     const float *rxyz = pinXyz_;

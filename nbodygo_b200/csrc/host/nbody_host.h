@@ -78,6 +78,9 @@ struct Body {
     // fragcalc.go:54-83: called with the factors the device computed (NB_EV_FRAGMENT)
     void DoFragment(Body &other, double thisFactor, double otherFactor);
     void initiateFragmentation(double fragFactor);
+    // the same with the Mass and position the body had when the event was handled (NB_EV_FRAG_INIT record +
+    // nb_get_cycle_top_positions): the device resolves the queue, the host only keeps fragInfo
+    void initiateFragmentationAt(double fragFactor, double massThen, double x, double y, double z);
     // fragcalc.go:90-117: spawns up to maxFragsPerCycle+1 bodies per cycle into bc (as add events)
     void fragment(BodyCollection &bc);
 };

@@ -974,6 +974,21 @@ extern "C" int nb_get_pairs(nb_handle h, int32_t *i, int32_t *j, int64_t cap, in
     return NB_OK;
 }
 
+extern "C" int nb_get_cycle_top_positions(nb_handle h, int64_t first, int64_t count, double *x, double *y, double *z)
+{
+    if (!h || first < 0 || count < 0 || first + count > h->n) return fail(h, NB_ERR_INVALID, "nb_get_cycle_top_positions: bad range");
+    if (!h->stepped) return fail(h, NB_ERR_INVALID, "nb_get_cycle_top_positions: no step since the array last changed");
+    NB_CUDA(h, cudaSetDevice(h->device));
+    // the j-stream K0 built for the last cycle: the positions Compute and ProcessMods saw
+    const size_t fb = (size_t)count * sizeof(double);
+    int rc = copy_out(h, x, h->d.jx + first, fb);
+    if (!rc) rc = copy_out(h, y, h->d.jy + first, fb);
+    if (!rc) rc = copy_out(h, z, h->d.jz + first, fb);
+    if (rc) return rc;
+    NB_CUDA(h, cudaStreamSynchronize(h->st));
+    return NB_OK;
+}
+
 extern "C" int nb_get_host_events(nb_handle h, nb_event *ev, int64_t cap, int64_t *n)
 {
     if (!h || !n) return NB_ERR_INVALID;
@@ -985,8 +1000,19 @@ extern "C" int nb_get_host_events(nb_handle h, nb_event *ev, int64_t cap, int64_
     const unsigned long long c = std::min<unsigned long long>(h->h_ctr->n_hev, (unsigned long long)h->hev_cap);
     std::vector<nb_event> all(c);
     if (c) NB_CUDA(h, cudaMemcpy(all.data(), h->d.hev, c * sizeof(nb_event), cudaMemcpyDeviceToHost));
-    std::sort(all.begin(), all.end(), [](const nb_event &a, const nb_event &b) {
+    // NB_EV_FRAG_INIT records come in the reference's handling order: descending key (i, j) of the event that
+    // raised them (applied == 1: a is the event's b1 = i, 2: a is its b2 = j); within one event b1 before b2
+    auto key_of = [](const nb_event &e) {
+        const unsigned long long i = (unsigned)(e.applied == 2 ? e.b : e.a), j = (unsigned)(e.applied == 2 ? e.a : e.b);
+        return (i << 32) | j;
+    };
+    std::sort(all.begin(), all.end(), [&](const nb_event &a, const nb_event &b) {
         if (a.kind != b.kind) return a.kind < b.kind;
+        if (a.kind == NB_EV_FRAG_INIT) {
+            const unsigned long long ka = key_of(a), kb = key_of(b);
+            if (ka != kb) return ka > kb;
+            return a.applied < b.applied;
+        }
         if (a.a != b.a) return a.a < b.a;
         return a.b < b.b;
     });

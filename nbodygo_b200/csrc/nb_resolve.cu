@@ -191,8 +191,16 @@ __device__ void resolve_one(const StepParams &p, int a, int b, const ElasticGeo 
         if ((ba == NB_FRAGMENT && thisFactor > s.ff[a]) || (bb == NB_FRAGMENT && otherFactor > s.ff[b])) {
             // doFragment, fragcalc.go:54-61: the flag half happens here, in event order; the fragInfo
             // bookkeeping and the spawning of fragments are host work fed by this record
-            if (ba == NB_FRAGMENT && thisFactor > s.ff[a]) initiate_fragmentation(s, a, thisFactor);
-            if (bb == NB_FRAGMENT && otherFactor > s.ff[b]) initiate_fragmentation(s, b, otherFactor);
+            // one NB_EV_FRAG_INIT record per initiateFragmentation call, with the mass the body has at this point of
+            // the queue (fragInfo.mass = Mass / fragments, fragcalc.go:80-82)
+            if (ba == NB_FRAGMENT && thisFactor > s.ff[a]) {
+                push_host_event(p, NB_EV_FRAG_INIT, a, b, 1, s.mass[a], thisFactor, 0.0);
+                initiate_fragmentation(s, a, thisFactor);
+            }
+            if (bb == NB_FRAGMENT && otherFactor > s.ff[b]) {
+                push_host_event(p, NB_EV_FRAG_INIT, b, a, 2, s.mass[b], otherFactor, 0.0);
+                initiate_fragmentation(s, b, otherFactor);
+            }
             push_host_event(p, NB_EV_FRAGMENT, a, b, 1, 0.0, thisFactor, otherFactor);
             return;
         }

@@ -439,8 +439,20 @@ static void resolve_collision(orc_bodies *bc, int64_t a, int64_t b, sink *out)
                 /* doFragment, cmd/body/fragcalc.go:54-61 */
                 double ffa = bc->frag_factor ? bc->frag_factor[a] : 0;
                 double ffb = bc->frag_factor ? bc->frag_factor[b] : 0;
-                if (bc->behavior[a] == ORC_FRAGMENT && tf > ffa) initiate_fragmentation(bc, a, tf);
-                if (bc->behavior[b] == ORC_FRAGMENT && of > ffb) initiate_fragmentation(bc, b, of);
+                if (bc->behavior[a] == ORC_FRAGMENT && tf > ffa) {
+                    if (out) {
+                        sink_push(out, ORC_EV_FRAG_INIT, a, b, bc->mass[a]);
+                        if (out->n <= out->cap) { out->ev[out->n - 1].f1 = tf; out->ev[out->n - 1].f2 = 1; }
+                    }
+                    initiate_fragmentation(bc, a, tf);
+                }
+                if (bc->behavior[b] == ORC_FRAGMENT && of > ffb) {
+                    if (out) {
+                        sink_push(out, ORC_EV_FRAG_INIT, b, a, bc->mass[b]);
+                        if (out->n <= out->cap) { out->ev[out->n - 1].f1 = of; out->ev[out->n - 1].f2 = 2; }
+                    }
+                    initiate_fragmentation(bc, b, of);
+                }
                 if (out) {
                     sink_push(out, ORC_EV_FRAGMENT, a, b, 0);
                     if (out->n <= out->cap) { out->ev[out->n - 1].f1 = tf; out->ev[out->n - 1].f2 = of; }

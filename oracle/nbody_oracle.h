@@ -47,7 +47,11 @@ enum { ORC_NONE = 0, ORC_SUBSUME = 1, ORC_ELASTIC = 2, ORC_FRAGMENT = 3 };
 #define ORC_F_COLLIDED 0x20u    /* Body.collided    cmd/body/body.go:51 */
 
 /* event kinds, cmd/body/event.go:20-24 (+ fragment hand-off record) */
-enum { ORC_EV_COLLISION = 0, ORC_EV_SUBSUME = 1, ORC_EV_FRAGMENT = 2 };
+enum { ORC_EV_COLLISION = 0, ORC_EV_SUBSUME = 1, ORC_EV_FRAGMENT = 2,
+       /* initiateFragmentation (fragcalc.go:66-83) ran for body a (partner b): dist = a's mass at that point of the
+        * queue, f1 = the fragFactor it was called with, f2 = 1 if a is the event's b1 else 2.  Pushed in handling
+        * order, before the ORC_EV_FRAGMENT record of the same event. */
+       ORC_EV_FRAG_INIT = 3 };
 
 /* Structure-of-arrays view of []*Body (cmd/body/body.go:34-52). All arrays
  * have at least n entries; the oracle never allocates or frees them. */

@@ -23,7 +23,7 @@ OPT_DEAD_J_SUBSUME = 0x8
 # no-ops in ResolveCollision); subsume events do not (ResolveSubsume has no Exists gate)
 OPT_CANONICAL = OPT_DEAD_J_SUBSUME
 
-EV_COLLISION, EV_SUBSUME, EV_FRAGMENT = 0, 1, 2
+EV_COLLISION, EV_SUBSUME, EV_FRAGMENT, EV_FRAG_INIT = 0, 1, 2, 3
 
 _DP = C.POINTER(C.c_double)
 _U8P = C.POINTER(C.c_uint8)
@@ -169,7 +169,7 @@ class OracleSim:
     def process_mods(self, events=None):
         ev = self.events if events is None else events
         ev = np.ascontiguousarray(ev)
-        out = np.zeros(max(16, len(ev)), dtype=EVENT_DTYPE)
+        out = np.zeros(max(16, 3 * len(ev)), dtype=EVENT_DTYPE)
         n_out = C.c_int64(0)
         s = self._struct()
         rc = lib().orc_process_mods(C.byref(s), ev.ctypes.data_as(C.POINTER(OrcEvent)), len(ev),

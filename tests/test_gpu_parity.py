@@ -303,6 +303,45 @@ def test_fragment_decisions_are_handed_to_host(capi):
     sim.close()
 
 
+def test_fragmentation_is_recorded_at_event_time(capi):
+    """initiateFragmentation (fragcalc.go:66-83) reads the body's Mass and position while the queue is processed:
+    after the subsumes handled earlier in the queue, before Update moves the body.  One NB_EV_FRAG_INIT record per
+    call, in the reference's handling order, with that mass; nb_get_cycle_top_positions returns the positions
+    ProcessMods saw.  Subsume bodies in the scene make the event-time mass differ from the mass after the cycle."""
+    from oracle.oracle import EV_FRAG_INIT
+    rng = np.random.default_rng(19)
+    n = 500
+    b = clouds.uniform_cube(n, 40.0, 1.0, 1e12, vmax=500.0, seed=29)
+    b.radius[:] = rng.uniform(0.8, 4.0, n)
+    b.mass[:] = rng.uniform(1e11, 1e13, n)
+    b.behavior[::3] = FRAGMENT
+    b.behavior[1::7] = SUBSUME
+    b.frag_factor[:] = 0.05
+    b.frag_step[:] = 100.0
+    x0 = b.x.copy()
+    o = oracle_sim(b.copy())
+    o.compute()
+    o.process_mods()
+    ref = [(int(e["a"]), int(e["b"]), int(e["f2"]), float(e["dist"]), float(e["f1"]))
+           for e in o.host_events if e["kind"] == EV_FRAG_INIT]
+    assert len(ref) > 10
+    sim = capi.Sim(n)
+    sim.upload(b)
+    sim.step(1e-6, 1.0)
+    got = [(int(e["a"]), int(e["b"]), int(e["applied"]), float(e["dist"]), float(e["f1"]))
+           for e in sim.host_events() if e["kind"] == capi.EV_FRAG_INIT]
+    # same calls, same order (the reference's handling order), the mass of that moment bit for bit
+    assert [g[:4] for g in got] == [r[:4] for r in ref]
+    assert np.allclose([g[4] for g in got], [r[4] for r in ref], rtol=1e-9)
+    # some body's event-time mass is not the mass it ends the cycle with (a subsume later in the queue)
+    end_mass = sim.download().mass
+    assert any(end_mass[a] != m for a, _, _, m, _ in got) or not (b.behavior == SUBSUME).any()
+    # the positions ProcessMods saw: the uploaded ones, not the ones Update produced
+    px, _, _ = sim.cycle_top_positions(0, n)
+    assert np.array_equal(px, x0) and not np.array_equal(sim.download().x, x0)
+    sim.close()
+
+
 def test_dead_and_fragmenting_bodies(capi):
     b = clouds.uniform_cube(500, 50.0, 1.5, 1e12, vmax=5.0, seed=17)
     b.flags[[3, 77, 250]] = 0          # dead: no force from or on them, no events

@@ -34,3 +34,24 @@ sim.host_events()
 sim.download()
 print("sanitize_mixed ok:", tot, "n =", sim.count())
 sim.close()
+
+# 256-body tiles, the uniform-mass / per-body-mass split, deleted bodies in the array (dead_j_sweep), the range
+# downloads, nb_set_forces and the sharded-upload entry point on a single handle
+n2 = 20_000
+c = clouds.uniform_cube(n2, 200.0, 1.0, 1e12, vmax=100.0, seed=6)
+c.radius[:] = rng.uniform(0.5, 7.0, n2)
+c.behavior[rng.random(n2) < 0.3] = SUBSUME
+dead = rng.random(n2) < 0.1
+c.flags[dead] &= ~np.uint8(1)
+sim = capi.Sim(n2)
+sim.upload_shard(n2, 0, n2, c.x, c.y, c.z, c.vx, c.vy, c.vz, c.mass, c.radius, behavior=c.behavior, flags=c.flags)
+for _ in range(2):
+    r = sim.step(1e-4, 0.9)
+fx, fy, fz = sim.forces()
+sim.set_forces(100, 50, fx[100:150], fy[100:150], fz[100:150])
+xs = np.zeros(500)
+sim.download_range_into(1000, 500, x=xs)
+xyz, ex = np.zeros((500, 3), dtype=np.float32), np.zeros(500, dtype=np.uint8)
+sim.render_range(1000, 500, xyz, ex)
+print("sanitize_mixed (large tiles, dead bodies) ok: subsumed", r.n_subsumed, "dead", r.n_dead, "events", r.n_host_events)
+sim.close()

@@ -648,3 +648,43 @@ def test_no_integrate_is_side_effect_free_on_state(capi):
     assert np.array_equal(g.flags, b.flags)
     assert len(sim.pairs()) > 0
     sim.close()
+
+
+def test_range_calls_and_force_roundtrip(capi):
+    """The round-2 ABI additions on one GPU: nb_upload_shard (== nb_upload on a single handle),
+    nb_download_state_range / nb_download_render_range, nb_set_forces, nb_comm_mode, and their argument checks."""
+    b = clouds.uniform_cube(700, 60.0, 2.0, 1e15, vmax=10.0, seed=31)
+    ref = capi.Sim(b.n)
+    ref.upload(b)
+    sim = capi.Sim(b.n)
+    sim.upload_shard(b.n, 0, b.n, b.x, b.y, b.z, b.vx, b.vy, b.vz, b.mass, b.radius, rest=b.rest,
+                     ff=b.frag_factor, fs=b.frag_step, behavior=b.behavior, flags=b.flags)
+    assert sim.comm_mode() == capi.COMM_SINGLE
+    with pytest.raises(capi.NbError):      # not this handle's i-range
+        sim.upload_shard(b.n, 10, b.n - 10, *[a[10:] for a in (b.x, b.y, b.z, b.vx, b.vy, b.vz, b.mass, b.radius)])
+    for s in (ref, sim):
+        s.step(1e-3, 1.0)
+    full = ref.download()
+    x, vz = np.zeros(100), np.zeros(100)
+    sim.download_range_into(250, 100, x=x, vz=vz)
+    assert np.array_equal(x, full.x[250:350]) and np.array_equal(vz, full.vz[250:350])
+    xyz, ex = np.zeros((100, 3), dtype=np.float32), np.zeros(100, dtype=np.uint8)
+    sim.render_range(250, 100, xyz, ex)
+    rxyz, rex = ref.render()
+    assert np.array_equal(xyz, rxyz[250:350]) and np.array_equal(ex, rex[250:350])
+    with pytest.raises(capi.NbError):
+        sim.download_range_into(650, 100, x=x)
+    # forces survive a host round trip (what a re-upload of a running collection does for fragmenting bodies)
+    fx, fy, fz = ref.forces()
+    sim.set_forces(0, b.n, np.zeros(b.n), np.zeros(b.n), np.zeros(b.n))
+    assert not sim.forces()[0].any()
+    sim.set_forces(5, 20, fx[5:25], fy[5:25], fz[5:25])
+    g = sim.forces()
+    assert np.array_equal(g[0][5:25], fx[5:25]) and np.array_equal(g[2][5:25], fz[5:25]) and not g[0][25:].any()
+    with pytest.raises(capi.NbError):
+        sim.set_forces(690, 20, fx[:20], fy[:20], fz[:20])
+    with pytest.raises(capi.NbError):      # compaction invalidates the cycle-top positions
+        sim.compact()
+        sim.cycle_top_positions(0, 10)
+    ref.close()
+    sim.close()

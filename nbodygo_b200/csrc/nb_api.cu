@@ -92,6 +92,7 @@ struct nb_sim {
     long long launches = 0;
     int force_R = 0;
     bool uniform_tiles = true;  // NB_UNIFORM_TILES=0 keeps every tile on the general (per-body mass) pass
+    int res_cluster = 8;        // CTAs of the resolve cluster (portable maximum); NB_RES_CLUSTER=1: one CTA as in round 1
     StepParams last_params{};
     // fused peer-memory exchange (K4 pushes the shard state into every peer's replica)
     bool peer_push = false;
@@ -175,7 +176,7 @@ static void free_all(nb_handle h)
     cudaFree(h->d.rs_ev); cudaFree(h->d.rs_list); cudaFree(h->d.rs_state);
     cudaFree(h->d.rs_queue); cudaFree(h->d.rs_cand); cudaFree(h->d.rs_active);
     cudaFree(h->d.rs_lkey); cudaFree(h->d.rs_pos); cudaFree(h->d.rs_candkey); cudaFree(h->d.rs_geo);
-    cudaFree(h->d.adj_off); cudaFree(h->d.adj_cnt);
+    cudaFree(h->d.adj_off); cudaFree(h->d.adj_cnt); cudaFree(h->d.rs_ctl);
     cudaFree(h->d.pairs); cudaFree(h->d.hev); cudaFree(h->d.head); cudaFree(h->d.ctr); cudaFree(h->d.zeros);
     cudaFree(h->scratch_f64); cudaFree(h->scratch_u8); cudaFree(h->d_map); cudaFree(h->d_new_n);
     cudaFree(h->d_block_sums); cudaFree(h->d_pair_counts);
@@ -231,6 +232,7 @@ extern "C" int nb_create(int device, int64_t capacity, int64_t pair_capacity, nb
     if (const char *fr = getenv("NB_FORCE_R")) h->force_R = atoi(fr);
     if (const char *g = getenv("NB_GRAPH")) h->graphs_enabled = atoi(g) != 0;
     if (const char *u = getenv("NB_UNIFORM_TILES")) h->uniform_tiles = atoi(u) != 0;
+    if (const char *c = getenv("NB_RES_CLUSTER")) h->res_cluster = std::max(1, std::min(8, atoi(c)));
     auto bail = [&](const char *what, cudaError_t ce) {
         g_create_err = std::string(what) + ": " + cudaGetErrorString(ce);
         free_all(h);
@@ -285,6 +287,8 @@ extern "C" int nb_create(int device, int64_t capacity, int64_t pair_capacity, nb
     NB_TRY(cudaMemsetAsync(h->d.adj_off, 0, (size_t)h->cap_pad * sizeof(int), h->st));
     NB_TRY(cudaMemsetAsync(h->d.adj_cnt, 0, (size_t)h->cap_pad * sizeof(int), h->st));
     NB_TRY(alloc_resolve_scratch(h, 1));
+    NB_TRY(cudaMalloc((void **)&h->d.rs_ctl, 8 * sizeof(int)));
+    NB_TRY(cudaMemsetAsync(h->d.rs_ctl, 0, 8 * sizeof(int), h->st));
     NB_TRY(cudaMalloc((void **)&h->d.zeros, 1024 * sizeof(unsigned)));
     NB_TRY(cudaMemsetAsync(h->d.zeros, 0, 1024 * sizeof(unsigned), h->st));
     NB_TRY(cudaMalloc((void **)&h->d.ctr, sizeof(Counters)));
@@ -754,6 +758,7 @@ extern "C" int nb_step(nb_handle h, double time_scaling, double R, uint32_t opts
     p.hev_cap = h->hev_cap;
     p.opts = opts;
     p.uniform_tiles = h->uniform_tiles ? 1 : 0;
+    p.res_cluster = h->res_cluster;
     p.ts = time_scaling;
     p.R = R;
     int rc = ensure_partials(h, (long long)p.n_chunks * p.n_pad_local);

@@ -97,6 +97,7 @@ struct DevState {
     int *rs_cand;              // [2E] new-head candidates of a round
     int *rs_active;            // [2E] bodies that have events this step
     ElasticGeo *rs_geo;        // [E] geometry of the collision events
+    int *rs_ctl;               // [8] scheduling counters of the resolve cluster (active bodies, cursor, queue begin/end/tail)
     Counters *ctr;
     unsigned *zeros;           // 1024 zeros (opaque low words for the rsqrt seeds in K1)
 };
@@ -147,6 +148,7 @@ struct StepParams {
     long long hev_cap;
     unsigned opts;
     int uniform_tiles;   // 1: K0 marks uniform-mass tiles and K1 hoists the mass out of their pair loop
+    int res_cluster;     // CTAs of the resolve cluster (1..8)
     double ts, R;
 };
 

@@ -23,7 +23,11 @@
 // Go's / glibc's in the last ulp.
 #include <cstdlib>
 
+#include <cooperative_groups.h>
+
 #include "nb_internal.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace nb {
 
@@ -227,15 +231,28 @@ __device__ __forceinline__ unsigned long long ev_key(int2 pr)
     return ((unsigned long long)(unsigned)pr.x << 32) | (unsigned)(pr.y & EV_INDEX_MASK);
 }
 
+// Round 2: the kernel runs as ONE THREAD-BLOCK CLUSTER of up to 8 CTAs (8 SMs).  A wavefront wider than a CTA (C3
+// with 4x radii: ~900 events per round, 11.8 k events per cycle) used to be bound by one SM's FP64 / libm rate
+// (480 us of an 11 ms cycle on one GPU, a third of the cycle on eight, where K3 is replicated); with the cluster
+// the independent events of a round are spread over 4096 threads.  The round barrier is the hardware cluster
+// barrier (barrier.cluster, release/acquire at cluster scope: what a CTA wrote to global memory before it is
+// visible to every CTA after it), the five scheduling counters live in global memory (ctl[]).  Short lists
+// (fewer events than one CTA has threads) run on the first CTA alone with __syncthreads(), the others leave at
+// once: the small cycles keep their latency.  Which events share a round, and therefore every result bit, does not
+// depend on how many CTAs take part.
+enum { CTL_N_ACTIVE = 0, CTL_CURSOR, CTL_Q_BEGIN, CTL_Q_END, CTL_Q_TAIL, CTL_WORDS };
+
 template <int RES_THREADS>
 __global__ void __launch_bounds__(RES_THREADS) k_resolve(const __grid_constant__ StepParams p)
 {
     __shared__ int seg_start[MAX_RANKS + 1];
     __shared__ int overflow;
-    __shared__ int n_active, cursor, q_begin, q_end, q_tail;
     const DevState &s = p.s;
-    const int tid = threadIdx.x;
-    if (tid == 0) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const int cta = (int)cluster.block_rank();
+    const int tid_local = threadIdx.x;
+    volatile int *ctl = s.rs_ctl;
+    if (tid_local == 0) {
         int acc = 0, ov = s.ctr->overflow;
         for (int r = 0; r < p.nranks; ++r) {
             seg_start[r] = acc;
@@ -246,13 +263,26 @@ __global__ void __launch_bounds__(RES_THREADS) k_resolve(const __grid_constant__
         }
         seg_start[p.nranks] = acc;
         overflow = ov;
-        n_active = cursor = q_begin = q_end = q_tail = 0;
-        s.ctr->total_pairs = acc;
-        if (ov) s.ctr->overflow = 1;
+        if (cta == 0) {
+            s.ctr->total_pairs = acc;
+            if (ov) s.ctr->overflow = 1;
+            for (int k = 0; k < CTL_WORDS; ++k) ctl[k] = 0;
+        }
     }
     __syncthreads();
     const int total = seg_start[p.nranks];
-    if (overflow || total == 0) return;
+    if (overflow || total == 0) return;   // uniform over the cluster: every CTA computed the same numbers
+
+    // how many CTAs of the cluster work on this list
+    const int nct = total >= RES_THREADS ? (int)cluster.num_blocks() : 1;
+    if (cta >= nct) return;               // before any barrier: an exited CTA counts as arrived
+    const int tid = cta * RES_THREADS + tid_local;
+    const int nthreads = nct * RES_THREADS;
+    auto sync_all = [&]() {
+        if (nct > 1) cluster.sync();
+        else __syncthreads();
+    };
+    sync_all();   // ctl[] is zero for everybody
 
     auto slot = [&](int e) -> long long {
         int r = 0;
@@ -264,7 +294,7 @@ __global__ void __launch_bounds__(RES_THREADS) k_resolve(const __grid_constant__
     const bool report_only = (p.opts & (NB_STEP_NO_RESOLVE | NB_STEP_NO_INTEGRATE)) != 0;
     {
         int subs = 0;
-        for (int e = tid; e < total; e += RES_THREADS) {
+        for (int e = tid; e < total; e += nthreads) {
             const int2 pr = s.pairs_all[slot(e)];
             if (pr.y & EV_SUBSUME_BIT) {
                 ++subs;
@@ -279,24 +309,24 @@ __global__ void __launch_bounds__(RES_THREADS) k_resolve(const __grid_constant__
     //      A body's slice holds the keys of its events (rs_lkey) and their indices (rs_list); a resolved
     //      event is struck out of both of its slices (key 0), so finding a body's next head is one pass
     //      over contiguous keys.
-    for (int e = tid; e < total; e += RES_THREADS) {
+    for (int e = tid; e < total; e += nthreads) {
         const int2 pr = s.pairs_all[slot(e)];
         s.rs_ev[e] = pr;
         s.rs_state[e] = 0;
         const int i = pr.x, j = pr.y & EV_INDEX_MASK;
         if (!(pr.y & EV_SUBSUME_BIT)) s.rs_geo[e] = elastic_geometry(s, i, j);  // positions are fixed during ProcessMods
-        if (atomicAdd(&s.adj_cnt[i], 1) == 0) s.rs_active[atomicAdd(&n_active, 1)] = i;
-        if (atomicAdd(&s.adj_cnt[j], 1) == 0) s.rs_active[atomicAdd(&n_active, 1)] = j;
+        if (atomicAdd(&s.adj_cnt[i], 1) == 0) s.rs_active[atomicAdd((int *)&ctl[CTL_N_ACTIVE], 1)] = i;
+        if (atomicAdd(&s.adj_cnt[j], 1) == 0) s.rs_active[atomicAdd((int *)&ctl[CTL_N_ACTIVE], 1)] = j;
     }
-    __syncthreads();
-    const int na = n_active;
-    for (int a = tid; a < na; a += RES_THREADS) {
+    sync_all();
+    const int na = ctl[CTL_N_ACTIVE];
+    for (int a = tid; a < na; a += nthreads) {
         const int b = s.rs_active[a];
-        s.adj_off[b] = atomicAdd(&cursor, s.adj_cnt[b]);
+        s.adj_off[b] = atomicAdd((int *)&ctl[CTL_CURSOR], s.adj_cnt[b]);
         s.adj_cnt[b] = 0;  // refilled below
     }
-    __syncthreads();
-    for (int e = tid; e < total; e += RES_THREADS) {
+    sync_all();
+    for (int e = tid; e < total; e += nthreads) {
         const int2 pr = s.rs_ev[e];
         const int i = pr.x, j = pr.y & EV_INDEX_MASK;
         const unsigned long long key = ev_key(pr);
@@ -306,11 +336,11 @@ __global__ void __launch_bounds__(RES_THREADS) k_resolve(const __grid_constant__
         s.rs_list[pj] = e; s.rs_lkey[pj] = key;
         s.rs_pos[e] = make_int2(pi, pj);
     }
-    __syncthreads();
+    sync_all();
 
-    // largest pending key of body b's slice and the event that holds it (-1: none left).  Plain
-    // (L1) loads: every writer is a thread of this CTA and a __syncthreads() lies in between.  Eight
-    // independent loads per trip keep the pass at one or two memory latencies for usual slice lengths.
+    // largest pending key of body b's slice and the event that holds it (-1: none left).  Every writer is a
+    // thread of this cluster and a barrier lies in between.  Eight independent loads per trip keep the pass at
+    // one or two memory latencies for usual slice lengths.
     auto scan_head = [&](int b, int &arg) -> unsigned long long {
         const int off = s.adj_off[b], cnt = s.adj_cnt[b];
         const unsigned long long *keys = s.rs_lkey + off;
@@ -333,28 +363,28 @@ __global__ void __launch_bounds__(RES_THREADS) k_resolve(const __grid_constant__
     };
 
     // ---- first wavefront
-    for (int a = tid; a < na; a += RES_THREADS) {
+    for (int a = tid; a < na; a += nthreads) {
         const int b = s.rs_active[a];
         int arg;
         s.head[b] = scan_head(b, arg);
     }
-    __syncthreads();
-    for (int e = tid; e < total; e += RES_THREADS) {
+    sync_all();
+    for (int e = tid; e < total; e += nthreads) {
         if (heads_both(ev_key(s.rs_ev[e]))) {
             s.rs_state[e] = 1;
-            s.rs_queue[atomicAdd(&q_tail, 1)] = e;
+            s.rs_queue[atomicAdd((int *)&ctl[CTL_Q_TAIL], 1)] = e;
         }
     }
-    __syncthreads();
-    if (tid == 0) q_end = q_tail;
-    __syncthreads();
+    sync_all();
+    if (tid == 0) ctl[CTL_Q_END] = ctl[CTL_Q_TAIL];
+    sync_all();
 
     // ---- rounds: every event enters the queue exactly once, in wavefront order
     int rounds = 0;
-    while (q_begin < q_end) {
-        const int qb = q_begin, qe = q_end;
+    while (ctl[CTL_Q_BEGIN] < ctl[CTL_Q_END]) {
+        const int qb = ctl[CTL_Q_BEGIN], qe = ctl[CTL_Q_END];
         // 1. the events of a wavefront touch disjoint bodies: resolve them in parallel, strike them out
-        for (int f = qb + tid; f < qe; f += RES_THREADS) {
+        for (int f = qb + tid; f < qe; f += nthreads) {
             const int e = s.rs_queue[f];
             const int2 pr = s.rs_ev[e];
             const int2 pos = s.rs_pos[e];
@@ -363,14 +393,14 @@ __global__ void __launch_bounds__(RES_THREADS) k_resolve(const __grid_constant__
             s.rs_lkey[pos.x] = 0ull;
             s.rs_lkey[pos.y] = 0ull;
         }
-        __syncthreads();
+        sync_all();
         // 2. new heads for the bodies of the resolved events (two tasks per event); a thread keeps its
-        //    first task's candidate in registers, further tasks (wavefronts wider than the CTA) go
+        //    first task's candidate in registers, further tasks (wavefronts wider than the cluster) go
         //    through scratch
         const int tasks = 2 * (qe - qb);
         int c0 = -1;
         unsigned long long ck0 = 0ull;
-        for (int t = tid; t < tasks; t += RES_THREADS) {
+        for (int t = tid; t < tasks; t += nthreads) {
             const int2 pr = s.rs_ev[s.rs_queue[qb + (t >> 1)]];
             const int b = (t & 1) ? (pr.y & EV_INDEX_MASK) : pr.x;
             int arg;
@@ -379,22 +409,23 @@ __global__ void __launch_bounds__(RES_THREADS) k_resolve(const __grid_constant__
             if (t == tid) { c0 = arg; ck0 = hk; }
             else { s.rs_cand[2 * qb + t] = arg; s.rs_candkey[2 * qb + t] = hk; }
         }
-        __syncthreads();
+        sync_all();
         // 3. a new head that now heads both of its bodies joins the next wavefront (once)
-        for (int t = tid; t < tasks; t += RES_THREADS) {
+        for (int t = tid; t < tasks; t += nthreads) {
             const int c = t == tid ? c0 : s.rs_cand[2 * qb + t];
             if (c < 0) continue;
             const unsigned long long ck = t == tid ? ck0 : s.rs_candkey[2 * qb + t];
-            if (heads_both(ck) && atomicCAS(&s.rs_state[c], 0, 1) == 0) s.rs_queue[atomicAdd(&q_tail, 1)] = c;
+            if (heads_both(ck) && atomicCAS(&s.rs_state[c], 0, 1) == 0)
+                s.rs_queue[atomicAdd((int *)&ctl[CTL_Q_TAIL], 1)] = c;
         }
         ++rounds;
-        __syncthreads();
-        if (tid == 0) { q_begin = qe; q_end = q_tail; }
-        __syncthreads();
+        sync_all();
+        if (tid == 0) { ctl[CTL_Q_BEGIN] = qe; ctl[CTL_Q_END] = ctl[CTL_Q_TAIL]; }
+        sync_all();
     }
 
     // ---- leave the per-body scratch zeroed for the next step
-    for (int a = tid; a < na; a += RES_THREADS) {
+    for (int a = tid; a < na; a += nthreads) {
         const int b = s.rs_active[a];
         s.head[b] = 0ull;
         s.adj_cnt[b] = 0;
@@ -427,16 +458,34 @@ int launch_push_pairs(const StepParams &p, cudaStream_t st)
     return 1;
 }
 
+template <int T>
+static void launch_resolve_cluster(const StepParams &p, cudaStream_t st, int cluster)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)cluster);
+    cfg.blockDim = dim3(T);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cluster;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, k_resolve<T>, p);
+}
+
 int launch_resolve(const StepParams &p, cudaStream_t st)
 {
     static const int threads = [] {  // development override
         const char *e = getenv("NB_RES_THREADS");
         return e ? atoi(e) : RES_THREADS_DEFAULT;
     }();
+    const int cluster = p.res_cluster < 1 ? 1 : (p.res_cluster > 8 ? 8 : p.res_cluster);
     switch (threads) {
-        case 1024: k_resolve<1024><<<1, 1024, 0, st>>>(p); break;
-        case 256: k_resolve<256><<<1, 256, 0, st>>>(p); break;
-        default: k_resolve<RES_THREADS_DEFAULT><<<1, RES_THREADS_DEFAULT, 0, st>>>(p); break;
+        case 1024: launch_resolve_cluster<1024>(p, st, cluster); break;
+        case 256: launch_resolve_cluster<256>(p, st, cluster); break;
+        default: launch_resolve_cluster<RES_THREADS_DEFAULT>(p, st, cluster); break;
     }
     return 1;
 }

@@ -688,3 +688,38 @@ def test_range_calls_and_force_roundtrip(capi):
         sim.cycle_top_positions(0, 10)
     ref.close()
     sim.close()
+
+
+def test_resolve_cluster_equals_single_cta(capi, monkeypatch):
+    """K3 runs as a thread-block cluster of 8 CTAs when the event list is longer than one CTA (round 2); which
+    events share a round — and therefore every bit of the result — must not depend on the number of CTAs.
+    Dense cloud: several thousand events in a dozen rounds, subsume chains and fragment decisions included."""
+    rng = np.random.default_rng(37)
+    n = 6000
+    b = clouds.uniform_cube(n, 95.0, 2.5, 1e12, vmax=100.0, seed=39)
+    b.radius[:] = rng.uniform(1.0, 4.0, n)
+    b.behavior[rng.random(n) < 0.1] = SUBSUME
+    b.behavior[rng.random(n) < 0.1] = FRAGMENT
+    b.frag_factor[:] = 0.05
+    b.frag_step[:] = 100.0
+    outs = []
+    for cluster in ("1", "8", "3"):
+        monkeypatch.setenv("NB_RES_CLUSTER", cluster)      # read at nb_create
+        sim = capi.Sim(n)
+        sim.upload(b)
+        log = []
+        for _ in range(3):
+            res = sim.step(1e-4, 0.9)
+            st = sim.download()
+            log.append((res.n_pairs, res.n_resolved, res.n_subsumed, res.resolve_rounds, st.vx.copy(), st.vz.copy(),
+                        st.mass.copy(), st.flags.copy(), st.behavior.copy(),
+                        [tuple(e) for e in sim.host_events().tolist()]))
+        sim.close()
+        outs.append(log)
+    assert outs[0][0][0] > 2000 and outs[0][0][3] > 3       # longer than one CTA, several rounds
+    for other in outs[1:]:
+        for a, c in zip(outs[0], other):
+            assert a[:4] == c[:4]
+            for x, y in zip(a[4:9], c[4:9]):
+                assert np.array_equal(x.view(np.uint8), y.view(np.uint8))
+            assert a[9] == c[9]

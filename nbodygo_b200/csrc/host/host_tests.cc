@@ -419,6 +419,7 @@ static void TestCapacityGrows()
         CHECK(cr.Stepper().stats().failed == 0 && cr.Computations() == 5);
         CHECK(cr.Stepper().Capacity() >= bc.Count());
         while (rqh.Next().second) {}
+        cr.Stepper().SyncToHost(bc);  // the device owns the positions between syncs
         for (auto &b : bc.GetArray()) xs->push_back(b->X);
     };
     uint64_t g_small = 0, g_big = 0;

@@ -25,6 +25,10 @@ def test_reference_arm_json_line():
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"] > 0
     assert d["vs_baseline"] is None and d["higher_is_better"] is True
     assert "workload" in d["config"] and "model" not in d["config"]
+    # both arms describe the workload with the same `config` object (the driver compares them)
+    sys.path.insert(0, ROOT)
+    import bench
+    assert d["config"] == bench.workload_config("C4", 20000, 1, 1e-9)
 
 
 def test_reference_arm_other_ranks_print_nothing():

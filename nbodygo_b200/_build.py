@@ -42,6 +42,19 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return SO
 
 
+def build_variant_full(name: str, flags: str) -> str:
+    """Development only: the whole library compiled with extra -D knobs (for knobs that touch nb_internal.cuh)."""
+    vdir = os.path.join(PKG, "variants")
+    os.makedirs(vdir, exist_ok=True)
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    so = os.path.join(vdir, f"libnbody_b200_{name}.so")
+    cmd = [nvcc, *NVCC_FLAGS, *flags.split(), "-o", so, *[os.path.join(CSRC, s) for s in SOURCES], "-ldl"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+    return so
+
+
 def build_variant(name: str, force_flags: str) -> str:
     """Development only (tools/k1_hw_variants.py): a copy of the library whose nb_force.cu is compiled with extra
     -D knobs, as nbodygo_b200/variants/libnbody_b200_<name>.so.  The other translation units are compiled once."""

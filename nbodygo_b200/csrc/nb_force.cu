@@ -85,6 +85,24 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
         "r"(parity)
         : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_empty(uint64_t *bar, unsigned parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred q;\n"
+        "NB_EWAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 q, [%0], %1;\n"
+        "@q bra NB_EDONE;\n"
+        "bra NB_EWAIT;\n"
+        "NB_EDONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
 // MUFU.RSQ64H: ~2^-22 relative seed of 1/sqrt(x) from the high word of x
 __device__ __forceinline__ double rsqrt_seed(double x)
 {
@@ -148,6 +166,12 @@ __device__ __forceinline__ double rsqrt_seed_lo(double x, unsigned lo)
 //                 triples should gain 1.4 % (291 -> 287 cycles per 8 pairs); MEASURED it loses 0.7 %
 //                 (tools/k1_hw_variants.py, profiles/r2_k1_variants.txt): in this loop a three-register read costs
 //                 nothing, every extra non-FP64 instruction costs ~1.5 cycles.  Kept as a knob, off.
+//   NB_EXP_MBAR   1: a stage of the j pipeline is handed back to the producer through an "empty" mbarrier every
+//                 thread arrives on, instead of a __syncthreads() per tile (warps of a CTA may then run a tile apart;
+//                 with NB_EXP_NSTAGE=3 the producer waits for the tile before the last)
+#ifndef NB_EXP_MBAR
+#define NB_EXP_MBAR 0
+#endif
 //   NB_EXP_UNR4   unroll of the j-group loop of the production shape (R = 4); 2 costs registers and MOVs
 //   NB_EXP_LOOP   form of the j-group loop: 0 = index, 1 = pointer against its end, 2 = count down (both worse)
 #ifndef NB_EXP_UNR4
@@ -528,6 +552,12 @@ __global__ void __launch_bounds__(NT, MINB) k_force(const __grid_constant__ Step
     static_assert(TJ % 2 == 0 && R <= 16, "tile of j-pairs");
     __shared__ __align__(128) double sm[NSTAGE][4][TJ];
     __shared__ __align__(8) uint64_t bar[NSTAGE];
+#if NB_EXP_MBAR
+    __shared__ __align__(8) uint64_t ebar[NSTAGE];
+    constexpr int LOOK = NSTAGE >= 3 ? NSTAGE - 2 : 1;  // tiles in flight ahead of the one being consumed
+#else
+    constexpr int LOOK = NSTAGE - 1;
+#endif
     constexpr bool UNI = MODE == FORCE_UNI;
 
     const int tid = threadIdx.x;
@@ -548,6 +578,10 @@ __global__ void __launch_bounds__(NT, MINB) k_force(const __grid_constant__ Step
     if (tid == 0) {
 #pragma unroll
         for (int s = 0; s < NSTAGE; ++s) mbar_init(&bar[s], 1);
+#if NB_EXP_MBAR
+#pragma unroll
+        for (int s = 0; s < NSTAGE; ++s) mbar_init(&ebar[s], NT);
+#endif
         mbar_fence_init();
     }
     __syncthreads();
@@ -562,7 +596,7 @@ __global__ void __launch_bounds__(NT, MINB) k_force(const __grid_constant__ Step
         bulk_g2s(&sm[s][3][0], p.s.jm + j0, TJ * sizeof(double), &bar[s]);
     };
     if (tid == 0) {
-        for (int t = 0; t < NSTAGE - 1 && t < nt; ++t) issue(t);
+        for (int t = 0; t < LOOK && t < nt; ++t) issue(t);
     }
 
     double xi[R], yi[R], zi[R], ri[R];
@@ -586,7 +620,15 @@ __global__ void __launch_bounds__(NT, MINB) k_force(const __grid_constant__ Step
 
     for (int t = 0; t < nt; ++t) {
         const int s = t % NSTAGE;
+#if NB_EXP_MBAR
+        if (tid == 0 && t + LOOK < nt) {
+            const int tn = t + LOOK, tc = tn - NSTAGE;  // tc: the tile that used that stage before
+            if (tc >= 0) mbar_wait_empty(&ebar[tn % NSTAGE], (unsigned)((tc / NSTAGE) & 1));
+            issue(tn);
+        }
+#else
         if (tid == 0 && t + NSTAGE - 1 < nt) issue(t + NSTAGE - 1);
+#endif
 
         // Conservative per-body screen for this tile: a pair (i,j) can only overlap (or be
         // degenerate) if hi(d2) < thr_i, thr_i = hi((r_i + rmax_tile)^2 (1+2^-18)) + 2.
@@ -700,7 +742,11 @@ __global__ void __launch_bounds__(NT, MINB) k_force(const __grid_constant__ Step
             ay[r] = __dadd_rn(ay[r], ty[r]);
             az[r] = __dadd_rn(az[r], tz[r]);
         }
+#if NB_EXP_MBAR
+        mbar_arrive(&ebar[s]);  // this thread is done with stage s
+#else
         __syncthreads();  // every warp is done with stage s before it is refilled
+#endif
     }
 
     // one partial-sum slot per (chunk, body); G*m_i is applied by the integrate kernel

@@ -24,10 +24,16 @@ namespace nb {
 // bodies per j-tile (one TMA bulk copy per field and tile).  Small collections use small tiles so
 // that the sweep has enough independent (i-block, j-chunk) work items; the choice is a function of
 // n only (chunking() in nb_api.cu), like everything that fixes the per-body summation order.
-constexpr int TJ_LARGE = 256, TJ_SMALL = 64;
+#ifndef NB_EXP_TJ_LARGE
+#define NB_EXP_TJ_LARGE 256   // experiment knob (tools/k1_hw_variants.py); 256 is the production tile
+#endif
+constexpr int TJ_LARGE = NB_EXP_TJ_LARGE, TJ_SMALL = 64;
 constexpr long long TJ_SMALL_BELOW = 16384;  // n < this uses TJ_SMALL
 constexpr int TJ = TJ_LARGE;                 // allocation granularity
-constexpr int NSTAGE = 2;    // smem stages of the j pipeline
+#ifndef NB_EXP_NSTAGE
+#define NB_EXP_NSTAGE 2
+#endif
+constexpr int NSTAGE = NB_EXP_NSTAGE;    // smem stages of the j pipeline
 // j-chunks per body (= partial-sum slots; a function of n only, see chunking() in nb_api.cu)
 constexpr int MIN_CHUNKS = 32;
 constexpr int MAX_CHUNKS = 64;  // more slots cost K4 more than they gain K1 (tools/chunk_sweep.py: n = 32 k cycle 1114 -> 1092 us)

@@ -9,6 +9,7 @@ Each variant is timed on the C4 cloud with the uniform-mass pass (all chunks uni
 NB_UNIFORM_TILES=0 (per-body-mass pass); best of 4 launches each."""
 import json
 import os
+
 import subprocess
 import sys
 
@@ -16,15 +17,14 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 VARIANTS = {
-    "r1": "-DNB_EXP_KREG=0",
     "prod": "",
-    "kz": "-DNB_EXP_KZ=1",
-    "kz_acc3": "-DNB_EXP_KZ=1 -DNB_EXP_ACC=3",
-    "kz_poly": "-DNB_EXP_KZ=1 -DNB_EXP_POLY=1",
-    "kz_lo": "-DNB_EXP_KZ=1 -DNB_EXP_LO=1",
-    "kz_unr2": "-DNB_EXP_KZ=1 -DNB_EXP_UNR4=2",
-    "unr2": "-DNB_EXP_UNR4=2",
+    "mbar2": "-DNB_EXP_MBAR=1",
+    "mbar3": "-DNB_EXP_MBAR=1 -DNB_EXP_NSTAGE=3",
+    "tj512": "-DNB_EXP_TJ_LARGE=512",
+    "tj512_mbar2": "-DNB_EXP_TJ_LARGE=512 -DNB_EXP_MBAR=1",
+    "nstage3": "-DNB_EXP_NSTAGE=3",
 }
+FULL = ("TJ_LARGE", "NSTAGE")     # knobs that live in nb_internal.cuh: rebuild every translation unit
 
 
 def child(n):
@@ -38,6 +38,8 @@ def child(n):
         o = capi.STEP_COLLISIONS | capi.STEP_NO_INTEGRATE | capi.STEP_PHASE_TIMINGS
         sim.step(1e-9, 1.0, o)
         out["uni" if uni else "gen"] = min(sim.step(1e-9, 1.0, o).ms_force for _ in range(4))
+        fx, fy, fz = sim.forces()
+        out["chk_" + ("uni" if uni else "gen")] = [float(abs(fx).sum()), float(abs(fz).sum()), int(len(sim.pairs()))]
         sim.close()
     print(json.dumps(out))
 
@@ -52,7 +54,7 @@ def main():
         sys.path.insert(0, os.path.join(ROOT, "tools"))
         import sass_model
         for name, flags in VARIANTS.items():
-            so = _build.build_variant(name, flags)
+            so = (_build.build_variant_full if any(k in flags for k in FULL) else _build.build_variant)(name, flags)
             unr = "2" if "UNR4=2" in flags else "1"
             rows = {r[0].split("ELi256ELi")[1][0]: (r[6], r[2], r[2] - r[4])
                     for r in sass_model.hot_loops(so, f"k_forceILi4ELi128ELi1ELi{unr}ELi256") if not r[3].get("SEL", 0)}
@@ -73,8 +75,11 @@ def main():
             print(name, "failed:", r.stderr[-300:])
             continue
         base = base or t
+        ok = all(abs(a - b) <= 1e-12 * abs(b) for k in ("chk_uni", "chk_gen") for a, b in zip(t[k][:2], base[k][:2])) \
+            and t["chk_uni"][2] == base["chk_uni"][2] == t["chk_gen"][2]
         print(f"{name:14s} uniform {t['uni']:9.3f} ms ({100 * (t['uni'] / base['uni'] - 1):+5.2f} %)   "
-              f"general {t['gen']:9.3f} ms ({100 * (t['gen'] / base['gen'] - 1):+5.2f} %)", flush=True)
+              f"general {t['gen']:9.3f} ms ({100 * (t['gen'] / base['gen'] - 1):+5.2f} %)   "
+              f"sum|F| and pair count agree with the first variant: {ok}", flush=True)
 
 
 if __name__ == "__main__":

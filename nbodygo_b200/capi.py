@@ -325,11 +325,12 @@ def uniform_chunks(b: BodyArrays):
     — bodies that do not exist, non-finite positions, the tail of the last tile — are parked far away
     and match any mass; a fragmenting body stays in place with effective mass 0 and breaks it);
     a chunk runs the uniform-mass pass if all its tiles are.  Collections below 16,384 bodies use
-    64-body tiles and a single per-body-mass launch (returns 0 uniform chunks for them)."""
+    64-body tiles and a single per-body-mass launch (returns 0 uniform chunks for them); from 786,432
+    bodies up the tiles hold 512 bodies."""
     from .bodies import F_EXISTS, F_FRAGMENTING
     n = b.n
     _, _, n_chunks, tpc = plan(n)
-    tj = 64 if n < 16384 else 256
+    tj = 64 if n < 16384 else (512 if n >= 786432 else 256)
     n_tiles = (n + tj - 1) // tj
     with np.errstate(invalid="ignore"):
         finite = (np.abs(b.x) < 1e150) & (np.abs(b.y) < 1e150) & (np.abs(b.z) < 1e150)

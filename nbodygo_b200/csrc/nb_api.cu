@@ -563,7 +563,7 @@ static void chunking(long long n, int &tj, int &n_tiles, int &n_chunks, int &til
     // a function of n only: the per-body summation order never depends on the grid or the rank count
     long long small_below = TJ_SMALL_BELOW;
     if (const char *e = getenv("NB_TJ_SMALL_BELOW")) small_below = atoll(e);  // development override
-    tj = n < small_below ? TJ_SMALL : TJ_LARGE;
+    tj = n < small_below ? TJ_SMALL : (n >= LARGE_N_BELOW ? TJ_HUGE : TJ_LARGE);
     n_tiles = (int)((n + tj - 1) / tj);
     // enough chunks that the CTA grid has >= ~40 rounds per SM (tail < ~1 %), within [32, MAX_CHUNKS]
     long long want = n > 0 ? (CHUNK_TARGET_CTAS * 512 + n - 1) / n : 1;

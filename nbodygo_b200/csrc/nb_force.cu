@@ -5,7 +5,7 @@
 // reference fans out over goroutines (cmd/runner/workpool.go:103-110).
 //
 // K1 layout: one CTA = NT threads x R register-blocked i-bodies, one j-chunk.
-// j-tiles (TJ bodies of jx,jy,jz,jm = 4 x 2 KB) are staged into shared memory with
+// j-tiles (TJ = 64 / 256 / 512 bodies of jx,jy,jz,jm) are staged into shared memory with
 // 1-D TMA bulk copies (cp.async.bulk + mbarrier, SASS UBLKCP), double buffered, and
 // read two bodies at a time with broadcast LDS.128.
 //
@@ -311,6 +311,7 @@ int launch_prep(const StepParams &p, cudaStream_t st)
 {
     if (p.n_tiles <= 0) return 0;
     if (p.tj == TJ_SMALL) k_prep<TJ_SMALL><<<p.n_tiles, TJ_SMALL, 0, st>>>(p);
+    else if (p.tj == TJ_HUGE) k_prep<TJ_HUGE><<<p.n_tiles, TJ_HUGE, 0, st>>>(p);
     else k_prep<TJ_LARGE><<<p.n_tiles, TJ_LARGE, 0, st>>>(p);
     return 1;
 }
@@ -550,6 +551,7 @@ template <int R, int NT, int MINB, int UNR, int TJ, int MODE>
 __global__ void __launch_bounds__(NT, MINB) k_force(const __grid_constant__ StepParams p)
 {
     static_assert(TJ % 2 == 0 && R <= 16, "tile of j-pairs");
+    constexpr int NSTAGE = NB_EXP_NSTAGE ? NB_EXP_NSTAGE : stages_for(TJ);
     __shared__ __align__(128) double sm[NSTAGE][4][TJ];
     __shared__ __align__(8) uint64_t bar[NSTAGE];
 #if NB_EXP_MBAR
@@ -777,11 +779,17 @@ static int launch_force_t(const StepParams &p, cudaStream_t st)
     }
     if (SPLIT && p.uniform_tiles) {
         // same grid twice: each CTA runs in the instantiation that matches its j-chunk and exits in the other
-        k_force<R, NT, MINB, UNR, TJ_LARGE, FORCE_UNI><<<grid, NT, 0, st>>>(p);
-        k_force<R, NT, MINB, UNR, TJ_LARGE, FORCE_MIXED><<<grid, NT, 0, st>>>(p);
+        if (p.tj == TJ_HUGE) {
+            k_force<R, NT, MINB, UNR, TJ_HUGE, FORCE_UNI><<<grid, NT, 0, st>>>(p);
+            k_force<R, NT, MINB, UNR, TJ_HUGE, FORCE_MIXED><<<grid, NT, 0, st>>>(p);
+        } else {
+            k_force<R, NT, MINB, UNR, TJ_LARGE, FORCE_UNI><<<grid, NT, 0, st>>>(p);
+            k_force<R, NT, MINB, UNR, TJ_LARGE, FORCE_MIXED><<<grid, NT, 0, st>>>(p);
+        }
         return 2;
     }
-    k_force<R, NT, MINB, UNR, TJ_LARGE, FORCE_ALL><<<grid, NT, 0, st>>>(p);
+    if (p.tj == TJ_HUGE) k_force<R, NT, MINB, UNR, TJ_HUGE, FORCE_ALL><<<grid, NT, 0, st>>>(p);
+    else k_force<R, NT, MINB, UNR, TJ_LARGE, FORCE_ALL><<<grid, NT, 0, st>>>(p);
     return 1;
 }
 

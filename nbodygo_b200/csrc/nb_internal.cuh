@@ -24,16 +24,20 @@ namespace nb {
 // bodies per j-tile (one TMA bulk copy per field and tile).  Small collections use small tiles so
 // that the sweep has enough independent (i-block, j-chunk) work items; the choice is a function of
 // n only (chunking() in nb_api.cu), like everything that fixes the per-body summation order.
-#ifndef NB_EXP_TJ_LARGE
-#define NB_EXP_TJ_LARGE 256   // experiment knob (tools/k1_hw_variants.py); 256 is the production tile
-#endif
-constexpr int TJ_LARGE = NB_EXP_TJ_LARGE, TJ_SMALL = 64;
-constexpr long long TJ_SMALL_BELOW = 16384;  // n < this uses TJ_SMALL
-constexpr int TJ = TJ_LARGE;                 // allocation granularity
+// Three tile sizes, chosen from n only: 64 below 16,384 bodies (enough independent work items for small
+// collections), 256 up to 786,431, 512 from there on — at 1 M bodies the per-tile work of K1 (barrier wait, per-body
+// screen thresholds, commit, __syncthreads) is 0.85 % of the sweep with 256-body tiles; measured -0.45 % with 512
+// (profiles/r2_k1_variants.txt).  The redo of a screened (body, tile) costs twice as much, which only matters for
+// dense small collections, and those use the small tiles.
+constexpr int TJ_HUGE = 512, TJ_LARGE = 256, TJ_SMALL = 64;
+constexpr long long TJ_SMALL_BELOW = 16384;  // n < this uses TJ_SMALL; n >= LARGE_N_BELOW uses TJ_HUGE
+constexpr int TJ = TJ_HUGE;                  // allocation granularity
+// smem stages of the j pipeline: 3 for the 64- and 256-body tiles (measured -0.1 % / -0.6 % on the uniform /
+// per-body-mass sweep against 2), 2 for the 512-body tiles (3 x 16 KB would pass the 48 KB of static shared memory)
+__host__ __device__ constexpr int stages_for(int tj) { return tj >= 512 ? 2 : 3; }
 #ifndef NB_EXP_NSTAGE
-#define NB_EXP_NSTAGE 2
+#define NB_EXP_NSTAGE 0   // experiment knob: force a stage count (0: stages_for)
 #endif
-constexpr int NSTAGE = NB_EXP_NSTAGE;    // smem stages of the j pipeline
 // j-chunks per body (= partial-sum slots; a function of n only, see chunking() in nb_api.cu)
 constexpr int MIN_CHUNKS = 32;
 constexpr int MAX_CHUNKS = 64;  // more slots cost K4 more than they gain K1 (tools/chunk_sweep.py: n = 32 k cycle 1114 -> 1092 us)
@@ -144,7 +148,7 @@ struct StepParams {
     long long n;         // bodies
     long long i0, i1;    // local i-shard
     long long n_pad_local;  // stride of partial-sum slots
-    int tj;              // tile size of this cycle: TJ_SMALL or TJ_LARGE
+    int tj;              // tile size of this cycle: TJ_SMALL, TJ_LARGE or TJ_HUGE
     int n_tiles;         // ceil(n / tj)
     int n_chunks;        // S
     int tiles_per_chunk;

@@ -16,17 +16,19 @@ sys.path.insert(0, os.path.join(ROOT, "tools"))
 
 pytestmark = pytest.mark.skipif(shutil.which("cuobjdump") is None, reason="cuobjdump not installed")
 
-PROD = "k_forceILi4ELi128ELi1ELi1ELi256"     # R = 4, 128 threads, 256-body tiles
+PROD = "k_forceILi4ELi128ELi1ELi1ELi256"     # R = 4, 128 threads, 256-body tiles (16,384 <= n < 786,432)
+PROD_HUGE = "k_forceILi4ELi128ELi1ELi1ELi512"  # the same with 512-body tiles (n >= 786,432: C4 runs these)
 
 
-@pytest.fixture(scope="module")
-def loops():
+@pytest.fixture(scope="module", params=[(PROD, "ELi256ELi"), (PROD_HUGE, "ELi512ELi")], ids=["tiles256", "tiles512"])
+def loops(request):
     import sass_model
     from nbodygo_b200 import _build
-    rows = sass_model.hot_loops(_build.build(), PROD)
+    prod, tag = request.param
+    rows = sass_model.hot_loops(_build.build(), prod)
     by = {}
     for name, addr, n, hist, n_fp64, three, cycles in rows:
-        mode = int(name.split("ELi256ELi")[1][0])          # FORCE_ALL 0, FORCE_MIXED 1, FORCE_UNI 2
+        mode = int(name.split(tag)[1][0])          # FORCE_ALL 0, FORCE_MIXED 1, FORCE_UNI 2
         by[(mode, bool(hist.get("SEL", 0)))] = dict(n=n, hist=hist, fp64=n_fp64, three=three, cycles=cycles)
     return by
 
@@ -69,8 +71,8 @@ def test_production_kernels_do_not_spill():
     lines = out.splitlines()
     seen = 0
     for i, line in enumerate(lines):
-        if PROD in line:
+        if PROD in line or PROD_HUGE in line:
             use = lines[i + 1]
             assert "STACK:0" in use and "LOCAL:0" in use, use
             seen += 1
-    assert seen == 3
+    assert seen == 6

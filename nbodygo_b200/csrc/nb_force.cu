@@ -85,24 +85,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, unsigned parity)
         "r"(parity)
         : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait_empty(uint64_t *bar, unsigned parity)
-{
-    asm volatile(
-        "{\n"
-        ".reg .pred q;\n"
-        "NB_EWAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 q, [%0], %1;\n"
-        "@q bra NB_EDONE;\n"
-        "bra NB_EWAIT;\n"
-        "NB_EDONE:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
-        : "memory");
-}
 // MUFU.RSQ64H: ~2^-22 relative seed of 1/sqrt(x) from the high word of x
 __device__ __forceinline__ double rsqrt_seed(double x)
 {
@@ -131,63 +113,32 @@ __device__ __forceinline__ double rsqrt_seed_lo(double x, unsigned lo)
     return y;
 }
 
-// Compile-time experiment knobs for tools/k1_variants.py (the defaults are the production code):
-//   NB_EXP_KREG   1 (production): the constant 15/8 lives in a register pair built from an opaque zero, so ptxas
-//                 cannot rematerialise it with two IMAD.MOV per loop trip: one instruction less per 8 pairs,
-//                 measured -0.55 % on the uniform-mass launch (60.03 -> 59.70 ms at n = 256 k)
-//   NB_EXP_POLY   1: w = s + s*(e*pp) instead of w = s*(1 + e*pp)
-//   NB_EXP_ACC    accumulate order inside a (body, j-pair) group: 0 = a.xyz then b.xyz, 1 = b then a,
-//                 2 = z y x, 3 = interleaved a.x b.x a.y b.y a.z b.z
+// Compile-time knobs of the hot loop (tools/k1_variants.py ranks builds offline by instruction counts,
+// tools/k1_hw_variants.py times them on the GPU; the defaults are the production code).  Round 2 measured ten
+// more source variants that are no longer in this file — accumulate order, polynomial form, where the running
+// minimum is updated, three loop forms, a padding instruction that moves ptxas' yield hints off the accumulate
+// triples, a stage hand-back through "empty" mbarriers — all of them slower or equal
+// (profiles/r2_k1_variants.txt; the code is in the history up to commit 61898ce).
+//   NB_EXP_KREG   1: the constant 15/8 lives in a register pair built from an opaque zero, so ptxas cannot
+//                 rematerialise it with two IMAD.MOV per loop trip: one instruction less per 8 pairs, measured
+//                 -0.55 % on the uniform-mass launch (60.03 -> 59.70 ms at n = 256 k)
+//   NB_EXP_KZ_GEN / NB_EXP_KZ_UNI   1: the constant gets an opaque zero of its own instead of sharing the first
+//                 seed's (one IMAD.MOV less per trip).  Measured at n = 256 k: the per-body-mass loop gains 0.4 %
+//                 with it, the uniform-mass loop LOSES 0.7 % — one instruction less, slower: at this level the
+//                 outcome is decided by how ptxas' schedule falls, not by counts.
+//   NB_EXP_UNR4   unroll of the j-group loop of the production shape (R = 4); 2 is rated 2.5 % faster by ptxas'
+//                 static schedule and measures 2 % slower (255 registers, nine extra MOVs)
 #ifndef NB_EXP_KREG
 #define NB_EXP_KREG 1
 #endif
-//   NB_EXP_KZ_GEN / NB_EXP_KZ_UNI   1: the constant gets an opaque zero of its own instead of sharing the first
-//                 seed's (one IMAD.MOV less per trip).  Measured at n = 256 k (profiles/r2_k1_variants.txt): the
-//                 per-body-mass loop gains 0.4 % with it, the uniform-mass loop LOSES 0.7 % — one instruction less,
-//                 slower: at this level the outcome is decided by how ptxas' schedule falls, not by counts.
 #ifndef NB_EXP_KZ_GEN
 #define NB_EXP_KZ_GEN 1
 #endif
 #ifndef NB_EXP_KZ_UNI
 #define NB_EXP_KZ_UNI 0
 #endif
-#ifndef NB_EXP_POLY
-#define NB_EXP_POLY 0
-#endif
-#ifndef NB_EXP_ACC
-#define NB_EXP_ACC 0
-#endif
-//   NB_EXP_LO     1: the running minimum of hi(d2) is updated after the accumulates (source order only)
-//   NB_EXP_PAD_GEN / NB_EXP_PAD_UNI   k: k extra one-cycle ALU instructions per loop trip of the per-body-mass /
-//                 uniform-mass loop (an opaque zero OR-ed into a dummy).  ptxas marks one instruction in every 12
-//                 issue cycles with a yield hint and never sets .reuse on it; when that instruction opens an
-//                 accumulate triple (w*dx, w*dy, w*dz share w through the reuse cache) the next one re-reads three
-//                 registers.  By the round-1 issue model one padding instruction that moves the hints off the
-//                 triples should gain 1.4 % (291 -> 287 cycles per 8 pairs); MEASURED it loses 0.7 %
-//                 (tools/k1_hw_variants.py, profiles/r2_k1_variants.txt): in this loop a three-register read costs
-//                 nothing, every extra non-FP64 instruction costs ~1.5 cycles.  Kept as a knob, off.
-//   NB_EXP_MBAR   1: a stage of the j pipeline is handed back to the producer through an "empty" mbarrier every
-//                 thread arrives on, instead of a __syncthreads() per tile (warps of a CTA may then run a tile apart;
-//                 with NB_EXP_NSTAGE=3 the producer waits for the tile before the last)
-#ifndef NB_EXP_MBAR
-#define NB_EXP_MBAR 0
-#endif
-//   NB_EXP_UNR4   unroll of the j-group loop of the production shape (R = 4); 2 costs registers and MOVs
-//   NB_EXP_LOOP   form of the j-group loop: 0 = index, 1 = pointer against its end, 2 = count down (both worse)
 #ifndef NB_EXP_UNR4
 #define NB_EXP_UNR4 1
-#endif
-#ifndef NB_EXP_LOOP
-#define NB_EXP_LOOP 0
-#endif
-#ifndef NB_EXP_LO
-#define NB_EXP_LO 0
-#endif
-#ifndef NB_EXP_PAD_GEN
-#define NB_EXP_PAD_GEN 0
-#endif
-#ifndef NB_EXP_PAD_UNI
-#define NB_EXP_PAD_UNI 0
 #endif
 
 // w = mj * d2^(-3/2) from the seed y0: with e = 1 - d2*y0^2 (|e| <~ 2^-21),
@@ -200,12 +151,8 @@ __device__ __forceinline__ double w_from_seed(double y0, double d2, double mj, d
     const double pp = __fma_rn(k1875, e, 1.5);
     const double t = __dmul_rn(mj, y0);
     const double tu = __dmul_rn(t, u);
-#if NB_EXP_POLY
-    return __fma_rn(tu, __dmul_rn(e, pp), tu);
-#else
     const double c = __fma_rn(e, pp, 1.0);
     return __dmul_rn(tu, c);
-#endif
 }
 
 // The same without the mass: d2^(-3/2) (6 FP64 ops), for tiles whose bodies all have one mass.
@@ -215,12 +162,8 @@ __device__ __forceinline__ double w_from_seed_uni(double y0, double d2, double k
     const double e = __fma_rn(-d2, u, 1.0);
     const double pp = __fma_rn(k1875, e, 1.5);
     const double s = __dmul_rn(y0, u);
-#if NB_EXP_POLY
-    return __fma_rn(s, __dmul_rn(e, pp), s);
-#else
     const double c = __fma_rn(e, pp, 1.0);
     return __dmul_rn(s, c);
-#endif
 }
 
 // ---------------------------------------------------------------- K0: prep
@@ -455,33 +398,13 @@ __device__ __forceinline__ void fast_tile(const double *sx, const double *sy, co
 #else
     const double k1875 = 1.875;
 #endif
-    constexpr int PAD = UNI ? NB_EXP_PAD_UNI : NB_EXP_PAD_GEN;
-    unsigned pad = 0u;
-#if NB_EXP_LOOP == 1
-    // one induction variable: the smem byte offset, compared against its end
-#pragma unroll(UNR)
-    for (const double *pj = sx, *const pe = sx + TJ; pj != pe; pj += 2) {
-        const int jj = (int)(pj - sx);
-#define NB_LD(arr) (*reinterpret_cast<const double2 *>(pj + ((arr) - sx)))
-#elif NB_EXP_LOOP == 2
-    // count down to zero
-#pragma unroll(UNR)
-    for (int kk = TJ / 2; kk > 0; --kk) {
-        const int jj = TJ - 2 * kk;
-#define NB_LD(arr) (*reinterpret_cast<const double2 *>((arr) + jj))
-#else
 #pragma unroll(UNR)
     for (int jj = 0; jj < TJ; jj += 2) {
-#define NB_LD(arr) (*reinterpret_cast<const double2 *>((arr) + jj))
-#endif
-#pragma unroll
-        for (int k = 0; k < PAD; ++k) asm volatile("or.b32 %0, %0, %1;" : "+r"(pad) : "r"(zlo[k % (2 * R)]));
-        const double2 vx = NB_LD(sx);
-        const double2 vy = NB_LD(sy);
-        const double2 vz = NB_LD(sz);
+        const double2 vx = *reinterpret_cast<const double2 *>(sx + jj);
+        const double2 vy = *reinterpret_cast<const double2 *>(sy + jj);
+        const double2 vz = *reinterpret_cast<const double2 *>(sz + jj);
         double2 vm = make_double2(0.0, 0.0);
-        if (!UNI) vm = NB_LD(sj);
-#undef NB_LD
+        if (!UNI) vm = *reinterpret_cast<const double2 *>(sj + jj);
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const double dxa = __dsub_rn(vx.x, xi[r]), dxb = __dsub_rn(vx.y, xi[r]);
@@ -499,46 +422,17 @@ __device__ __forceinline__ void fast_tile(const double *sx, const double *sy, co
                 ya = __hiloint2double(sa ? 0 : __double2hiint(ya), __double2loint(ya));
                 yb = __hiloint2double(sb ? 0 : __double2hiint(yb), __double2loint(yb));
             }
-#if !NB_EXP_LO
             lo[r] = min(lo[r], min(ha, hb));
-#endif
             const double wa = UNI ? w_from_seed_uni(ya, d2a, k1875) : w_from_seed(ya, d2a, vm.x, k1875);
             const double wb = UNI ? w_from_seed_uni(yb, d2b, k1875) : w_from_seed(yb, d2b, vm.y, k1875);
-#if NB_EXP_ACC == 1
-            tx[r] = __fma_rn(wb, dxb, tx[r]);
-            ty[r] = __fma_rn(wb, dyb, ty[r]);
-            tz[r] = __fma_rn(wb, dzb, tz[r]);
-            tx[r] = __fma_rn(wa, dxa, tx[r]);
-            ty[r] = __fma_rn(wa, dya, ty[r]);
-            tz[r] = __fma_rn(wa, dza, tz[r]);
-#elif NB_EXP_ACC == 2
-            tz[r] = __fma_rn(wa, dza, tz[r]);
-            ty[r] = __fma_rn(wa, dya, ty[r]);
-            tx[r] = __fma_rn(wa, dxa, tx[r]);
-            tz[r] = __fma_rn(wb, dzb, tz[r]);
-            ty[r] = __fma_rn(wb, dyb, ty[r]);
-            tx[r] = __fma_rn(wb, dxb, tx[r]);
-#elif NB_EXP_ACC == 3
-            tx[r] = __fma_rn(wa, dxa, tx[r]);
-            tx[r] = __fma_rn(wb, dxb, tx[r]);
-            ty[r] = __fma_rn(wa, dya, ty[r]);
-            ty[r] = __fma_rn(wb, dyb, ty[r]);
-            tz[r] = __fma_rn(wa, dza, tz[r]);
-            tz[r] = __fma_rn(wb, dzb, tz[r]);
-#else
             tx[r] = __fma_rn(wa, dxa, tx[r]);
             ty[r] = __fma_rn(wa, dya, ty[r]);
             tz[r] = __fma_rn(wa, dza, tz[r]);
             tx[r] = __fma_rn(wb, dxb, tx[r]);
             ty[r] = __fma_rn(wb, dyb, ty[r]);
             tz[r] = __fma_rn(wb, dzb, tz[r]);
-#endif
-#if NB_EXP_LO
-            lo[r] = min(lo[r], min(ha, hb));
-#endif
         }
     }
-    if (PAD) lo[0] = min(lo[0], ~pad);  // pad stays 0
 }
 
 // ---------------------------------------------------------------- K1: kernel
@@ -554,12 +448,7 @@ __global__ void __launch_bounds__(NT, MINB) k_force(const __grid_constant__ Step
     constexpr int NSTAGE = NB_EXP_NSTAGE ? NB_EXP_NSTAGE : stages_for(TJ);
     __shared__ __align__(128) double sm[NSTAGE][4][TJ];
     __shared__ __align__(8) uint64_t bar[NSTAGE];
-#if NB_EXP_MBAR
-    __shared__ __align__(8) uint64_t ebar[NSTAGE];
-    constexpr int LOOK = NSTAGE >= 3 ? NSTAGE - 2 : 1;  // tiles in flight ahead of the one being consumed
-#else
-    constexpr int LOOK = NSTAGE - 1;
-#endif
+    constexpr int LOOK = NSTAGE - 1;  // tiles in flight ahead of the one being consumed
     constexpr bool UNI = MODE == FORCE_UNI;
 
     const int tid = threadIdx.x;
@@ -580,10 +469,6 @@ __global__ void __launch_bounds__(NT, MINB) k_force(const __grid_constant__ Step
     if (tid == 0) {
 #pragma unroll
         for (int s = 0; s < NSTAGE; ++s) mbar_init(&bar[s], 1);
-#if NB_EXP_MBAR
-#pragma unroll
-        for (int s = 0; s < NSTAGE; ++s) mbar_init(&ebar[s], NT);
-#endif
         mbar_fence_init();
     }
     __syncthreads();
@@ -622,15 +507,7 @@ __global__ void __launch_bounds__(NT, MINB) k_force(const __grid_constant__ Step
 
     for (int t = 0; t < nt; ++t) {
         const int s = t % NSTAGE;
-#if NB_EXP_MBAR
-        if (tid == 0 && t + LOOK < nt) {
-            const int tn = t + LOOK, tc = tn - NSTAGE;  // tc: the tile that used that stage before
-            if (tc >= 0) mbar_wait_empty(&ebar[tn % NSTAGE], (unsigned)((tc / NSTAGE) & 1));
-            issue(tn);
-        }
-#else
-        if (tid == 0 && t + NSTAGE - 1 < nt) issue(t + NSTAGE - 1);
-#endif
+        if (tid == 0 && t + LOOK < nt) issue(t + LOOK);
 
         // Conservative per-body screen for this tile: a pair (i,j) can only overlap (or be
         // degenerate) if hi(d2) < thr_i, thr_i = hi((r_i + rmax_tile)^2 (1+2^-18)) + 2.
@@ -744,11 +621,7 @@ __global__ void __launch_bounds__(NT, MINB) k_force(const __grid_constant__ Step
             ay[r] = __dadd_rn(ay[r], ty[r]);
             az[r] = __dadd_rn(az[r], tz[r]);
         }
-#if NB_EXP_MBAR
-        mbar_arrive(&ebar[s]);  // this thread is done with stage s
-#else
         __syncthreads();  // every warp is done with stage s before it is refilled
-#endif
     }
 
     // one partial-sum slot per (chunk, body); G*m_i is applied by the integrate kernel

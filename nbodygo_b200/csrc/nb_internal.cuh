@@ -36,7 +36,7 @@ constexpr int TJ = TJ_HUGE;                  // allocation granularity
 // per-body-mass sweep against 2), 2 for the 512-body tiles (3 x 16 KB would pass the 48 KB of static shared memory)
 __host__ __device__ constexpr int stages_for(int tj) { return tj >= 512 ? 2 : 3; }
 #ifndef NB_EXP_NSTAGE
-#define NB_EXP_NSTAGE 0   // experiment knob: force a stage count (0: stages_for)
+#define NB_EXP_NSTAGE 0   // development knob (tools/k1_hw_variants.py): force a stage count (0: stages_for)
 #endif
 // j-chunks per body (= partial-sum slots; a function of n only, see chunking() in nb_api.cu)
 constexpr int MIN_CHUNKS = 32;

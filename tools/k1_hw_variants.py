@@ -16,15 +16,15 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-VARIANTS = {
+VARIANTS = {          # the knobs that are still in the source (the rejected ones are in the history, see nb_force.cu)
     "prod": "",
-    "mbar2": "-DNB_EXP_MBAR=1",
-    "mbar3": "-DNB_EXP_MBAR=1 -DNB_EXP_NSTAGE=3",
-    "tj512": "-DNB_EXP_TJ_LARGE=512",
-    "tj512_mbar2": "-DNB_EXP_TJ_LARGE=512 -DNB_EXP_MBAR=1",
-    "nstage3": "-DNB_EXP_NSTAGE=3",
+    "nokreg": "-DNB_EXP_KREG=0",
+    "kz_uni": "-DNB_EXP_KZ_UNI=1",
+    "nokz_gen": "-DNB_EXP_KZ_GEN=0",
+    "unr2": "-DNB_EXP_UNR4=2",
+    "nstage2": "-DNB_EXP_NSTAGE=2",
 }
-FULL = ("TJ_LARGE", "NSTAGE")     # knobs that live in nb_internal.cuh: rebuild every translation unit
+FULL = ("NSTAGE",)     # knobs that live in nb_internal.cuh: rebuild every translation unit
 
 
 def child(n):

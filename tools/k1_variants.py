@@ -1,9 +1,10 @@
 #!/usr/bin/env python3
 """Compiles nb_force.cu with experiment knobs (-DNB_EXP_*=..) to a cubin and prints the issue-model cost
-of K1's hot loops (tools/sass_model.py) — no GPU needed; the model reproduced the measured launch to
-0.1 % (profiles/r2_summary.md).
+of K1's hot loops (tools/sass_model.py) — no GPU needed.  Use it to rank by instruction COUNTS: round 2 showed
+that the model's cycle figure is off by up to 2 % in either direction (profiles/r2_k1_variants.txt), so a
+variant is only accepted after tools/k1_hw_variants.py has timed it.
 
-  python tools/k1_variants.py "" "-DNB_EXP_KREG=1" "-DNB_EXP_KREG=1 -DNB_EXP_ACC=2" ...
+  python tools/k1_variants.py "" "-DNB_EXP_KREG=0" "-DNB_EXP_KZ_UNI=1 -DNB_EXP_UNR4=2" ...
 """
 import os
 import subprocess

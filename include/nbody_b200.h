@@ -254,7 +254,8 @@ int nb_shard_range(nb_handle h, int64_t *i0, int64_t *i1);
 /* Pure planning function, usable without a device: the i-range [i0,i1) of `rank`
  * out of `nranks` for n bodies (contiguous ceil(n/nranks) slices,
  * computation-runner.go:286-293) and the j-chunking (partial-sum slots per body,
- * j-tiles of 256 bodies per chunk) — both functions of n only. */
+ * j-tiles per chunk; a tile holds 64 bodies below 16,384 bodies, 256 up to 786,431,
+ * 512 from there on) — all functions of n only. */
 int nb_plan(int64_t n, int rank, int nranks, int64_t *i0, int64_t *i1, int32_t *n_chunks,
             int32_t *tiles_per_chunk);
 

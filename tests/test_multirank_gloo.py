@@ -138,7 +138,8 @@ def test_plan_is_a_partition_and_depends_on_n_only():
             assert len({(nc, tpc) for _, _, nc, tpc in ranges}) == 1
             assert ranges[0][2:] == capi.plan(n, 0, 1)[2:]
         _, _, nc, tpc = capi.plan(n, 0, 1)
-        tiles = -(-n // 256)
+        tj = 64 if n < 16384 else (512 if n >= 786432 else 256)     # the tile size is a function of n only, too
+        tiles = -(-n // tj)
         assert 1 <= nc <= 128 and nc * tpc >= tiles
     with pytest.raises(capi.NbError):
         capi.plan(10, 2, 2)

@@ -70,3 +70,25 @@ def test_uniform_chunk_report_mirrors_the_device_rule():
     assert nu == nc and tu == nt                           # 100 k equal masses: every chunk
     c3.mass[::256] *= 1.5
     assert capi.uniform_chunks(c3)[0] == 0 and capi.uniform_chunks(c3)[2] == 0
+
+
+def test_header_is_plain_c_and_declares_what_the_library_exports(tmp_path):
+    """include/nbody_b200.h is the cgo boundary: it must compile as C (not only as C++), and every function it
+    declares must be an exported symbol of the built library (and listed in capi.SYMBOLS)."""
+    import re
+    import shutil
+    import subprocess
+    from nbodygo_b200 import _build, capi
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not installed")
+    hdr = os.path.join(ROOT, "include", "nbody_b200.h")
+    src = tmp_path / "t.c"
+    src.write_text('#include "nbody_b200.h"\nint main(void) { nb_step_result r; nb_event e; (void)r; (void)e; return nb_abi_version() == NB_ABI_VERSION ? 0 : 1; }\n')
+    r = subprocess.run(["gcc", "-std=c11", "-Wall", "-Wextra", "-Werror", "-pedantic", "-fsyntax-only",
+                        "-I", os.path.dirname(hdr), str(src)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    declared = set(re.findall(r"^(?:int|const char \*)\s*(nb_[a-z0-9_]+)\(", open(hdr).read(), flags=re.M))
+    assert declared == set(capi.SYMBOLS), declared ^ set(capi.SYMBOLS)
+    exported = subprocess.run(["nm", "-D", "--defined-only", _build.build()], capture_output=True, text=True).stdout
+    for sym in declared:
+        assert re.search(rf"\bT {sym}\b", exported), sym

@@ -6,6 +6,8 @@ import os
 import subprocess
 import sys
 
+import pytest
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 TOOL = os.path.join(ROOT, "tests", "parity", "compare_go_dump.py")
 
@@ -44,3 +46,26 @@ def test_a_flipped_bit_is_noticed(tmp_path):
     del lines[e]
     open(dump, "w").write("\n".join(lines) + "\n")
     assert cg.main(["--csv", csv, "--dump", dump, "--quiet"]) == 1
+
+
+def test_reference_side_patch_applies(tmp_path):
+    """integration/patches/nbodygo-gpu.patch (the edits to existing reference files: runner, builder, sim, server
+    flags) must apply cleanly to the reference tree.  Only where the tree exists (this container, not the GPU box);
+    the Go files next to it cannot be compiled here (no toolchain) — this keeps at least the patch honest."""
+    import shutil
+    ref = "/root/reference"
+    if not os.path.isdir(os.path.join(ref, "cmd", "runner")) or shutil.which("patch") is None:
+        pytest.skip("reference tree or patch(1) not available")
+    patch = os.path.join(ROOT, "integration", "patches", "nbodygo-gpu.patch")
+    files = [l[6:].strip() for l in open(patch) if l.startswith("+++ b/")]
+    assert "cmd/runner/computation-runner.go" in files and len(files) == 4
+    for f in files:
+        dst = tmp_path / f
+        dst.parent.mkdir(parents=True, exist_ok=True)
+        shutil.copy(os.path.join(ref, f), dst)
+    r = subprocess.run(["patch", "-p1", "--dry-run", "-i", patch], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 0 and "FAILED" not in r.stdout and "fuzz" not in r.stdout, r.stdout + r.stderr
+    # the new files do not collide with anything the reference already has
+    for f in ("cmd/runner/gpustepper.go", "cmd/runner/gpustepper_stub.go", "cmd/body/gpu_accessors.go",
+              "cmd/sim/parity_dump_test.go"):
+        assert os.path.exists(os.path.join(ROOT, "integration", f)) and not os.path.exists(os.path.join(ref, f))

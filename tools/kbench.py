@@ -23,6 +23,7 @@ def main():
     a = ap.parse_args()
     from nbodygo_b200 import capi, clouds
     b = clouds.config("C4", n=a.n)
+    os.environ.setdefault("NB_UNIFORM_TILES", "1")
     peak, _ = capi.measure_fp64_peak(0, 4096)
     print(f"n={a.n} fp64 peak measured {peak:.2f} TFLOP/s")
     ref = None

@@ -217,7 +217,8 @@ __device__ void resolve_one(const StepParams &p, int a, int b, const ElasticGeo 
     atomicAdd(&s.ctr->n_resolved, 1ull);
 }
 
-// One CTA.  Event e of the concatenated per-rank segments lives at pairs_all[rank*seg_stride + k].
+// One cluster of CTAs (see below).  Event e of the concatenated per-rank segments lives at
+// pairs_all[rank*seg_stride + k].
 //
 // Work-efficient wavefront: the events are first linked to their two bodies (an unsorted CSR built
 // with counting atomics), every body publishes the largest key of its list (head[]), and the events

@@ -417,7 +417,9 @@ def run_ours(args):
                 # time for the roofline comes from three more cycles with them.
                 base_opts = 0 if name == "C2" else capi.STEP_COLLISIONS
                 a2 = timed_cycles(s2, k, 3, base_opts)
-                a2["t_force"] = timed_cycles(s2, 3, 1, base_opts | capi.STEP_PHASE_TIMINGS)["t_force"]
+                slow = a2["t_dev"] / k > 0.5                      # 4 M bodies: one more cycle is enough
+                a2["t_force"] = timed_cycles(s2, 1 if slow else 3, 0 if slow else 1,
+                                             base_opts | capi.STEP_PHASE_TIMINGS)["t_force"]
                 s2.close()
                 it = interactions_of(b2.n)
                 ach = FLOPS_PER_INTERACTION * (it / world) / a2["t_force"] / 1e12

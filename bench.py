@@ -154,7 +154,7 @@ def run_reference(args):
     bodies = clouds.config(args.config, n=args.n or None)
     n = bodies.n
     workers = os.cpu_count() or 1
-    per_step_s = 6.0
+    per_step_s = 5.0
     for _ in range(max(args.warmup, 0)):
         cpu_pool_rate(bodies, 0.5, workers)
     tot_rows, tot_dt, sample = 0, 0.0, ""

@@ -26,19 +26,42 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+class _BuildLock:
+    """One builder at a time per checkout: several ranks of one job (torchrun) may all find the library stale
+    (a copy that did not keep the mtimes) — they must not write the same file concurrently."""
+
+    def __enter__(self):
+        import fcntl
+        self.f = open(os.path.join(PKG, ".build.lock"), "w")
+        fcntl.flock(self.f, fcntl.LOCK_EX)
+        return self
+
+    def __exit__(self, *exc):
+        import fcntl
+        fcntl.flock(self.f, fcntl.LOCK_UN)
+        self.f.close()
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return SO
-    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    extra = os.environ.get("NB_NVCC_EXTRA", "").split()
-    cmd = [nvcc, *NVCC_FLAGS, *extra, "-o", SO, *[os.path.join(CSRC, s) for s in SOURCES], "-ldl"]
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
-    if verbose:
-        print(r.stderr)
+    with _BuildLock():
+        if not force and not _stale():      # another rank built it while this one waited
+            return SO
+        nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+        extra = os.environ.get("NB_NVCC_EXTRA", "").split()
+        tmp = SO + f".tmp{os.getpid()}"
+        cmd = [nvcc, *NVCC_FLAGS, *extra, "-o", tmp, *[os.path.join(CSRC, s) for s in SOURCES], "-ldl"]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            if os.path.exists(tmp):
+                os.unlink(tmp)
+            raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+        os.replace(tmp, SO)                     # atomic: a reader never sees a half-written library
+        if verbose:
+            print(r.stderr)
     return SO
 
 
@@ -99,17 +122,20 @@ def build_host(force: bool = False) -> dict:
     deps = [os.path.join(HOST_DIR, f) for f in os.listdir(HOST_DIR)] + [SO]
     newest = max(os.path.getmtime(d) for d in deps)
     cxx = os.environ.get("CXX", "g++")
-    for name, main_src in HOST_BINARIES.items():
-        exe = os.path.join(BIN_DIR, name)
-        out[name] = exe
-        if not force and os.path.exists(exe) and os.path.getmtime(exe) >= newest:
-            continue
-        cmd = [cxx, "-std=c++17", "-O2", "-Wall", "-Wextra", "-o", exe,
-               *[os.path.join(HOST_DIR, s) for s in HOST_LIB_SOURCES], os.path.join(HOST_DIR, main_src),
-               "-L" + PKG, "-lnbody_b200", "-Wl,-rpath,$ORIGIN/..", "-lpthread"]
-        r = subprocess.run(cmd, capture_output=True, text=True)
-        if r.returncode != 0:
-            raise RuntimeError("g++ failed:\n" + r.stdout + r.stderr)
+    with _BuildLock():
+        for name, main_src in HOST_BINARIES.items():
+            exe = os.path.join(BIN_DIR, name)
+            out[name] = exe
+            if not force and os.path.exists(exe) and os.path.getmtime(exe) >= newest:
+                continue
+            tmp = exe + f".tmp{os.getpid()}"
+            cmd = [cxx, "-std=c++17", "-O2", "-Wall", "-Wextra", "-o", tmp,
+                   *[os.path.join(HOST_DIR, s) for s in HOST_LIB_SOURCES], os.path.join(HOST_DIR, main_src),
+                   "-L" + PKG, "-lnbody_b200", "-Wl,-rpath,$ORIGIN/..", "-lpthread"]
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if r.returncode != 0:
+                raise RuntimeError("g++ failed:\n" + r.stdout + r.stderr)
+            os.replace(tmp, exe)
     return out
 
 

@@ -203,6 +203,11 @@ void ResetIdGenerator()
     std::lock_guard<std::mutex> g(g_idLock);
     g_id = 0;
 }
+void SetNextId(int id)
+{
+    std::lock_guard<std::mutex> g(g_idLock);
+    g_id = id;
+}
 
 // ---------------------------------------------------------------- events
 Event NewAdd(BodyPtr b) { return Event{EventType::Add, nullptr, nullptr, std::move(b)}; }

@@ -90,6 +90,64 @@ bool WriteCsv(const std::string &csvPath, const std::vector<BodyPtr> &bodies)
     return true;
 }
 
+// ---------------------------------------------------------------- state sidecar (see RunState in nbody_host.h)
+bool WriteState(const std::string &path, const std::vector<BodyPtr> &bodies, const RunState &rs)
+{
+    FILE *f = std::fopen(path.c_str(), "w");
+    if (!f) return false;
+    std::fprintf(f, "#nbstate v1\t%zu\t%d\t%d\t%a\n", bodies.size(), rs.nextId, rs.cycle, rs.R);
+    for (auto &b : bodies)
+        std::fprintf(f, "%d\t%s\t%s\t%d\t%d\t%a\t%d\t%a\t%a\t%a\t%d\t%a\t%a\t%a\t%a\t%a\t%a\t%a\n", b->Id,
+                     b->Name.c_str(), b->Class.c_str(), b->Pinned ? 1 : 0, b->WithTelemetry ? 1 : 0, b->r,
+                     b->fragmenting ? 1 : 0, b->fragInfo.radius, b->fragInfo.newRadius, b->fragInfo.mass,
+                     b->fragInfo.fragments, b->fragInfo.x, b->fragInfo.y, b->fragInfo.z, b->fx, b->fy, b->fz,
+                     b->intensity);
+    std::fclose(f);
+    return true;
+}
+
+bool ReadState(const std::string &path, std::vector<BodyPtr> &bodies, RunState &rs)
+{
+    std::ifstream f(path);
+    if (!f) return false;
+    auto split = [](const std::string &line) {
+        std::vector<std::string> out;
+        size_t a = 0;
+        for (;;) {
+            const size_t t = line.find('\t', a);
+            out.push_back(line.substr(a, t == std::string::npos ? std::string::npos : t - a));
+            if (t == std::string::npos) break;
+            a = t + 1;
+        }
+        return out;
+    };
+    std::string line;
+    if (!std::getline(f, line)) return false;
+    const auto h = split(line);
+    if (h.size() != 5 || h[0] != "#nbstate v1" || (size_t)std::strtoull(h[1].c_str(), nullptr, 10) != bodies.size())
+        return false;
+    rs.nextId = std::atoi(h[2].c_str());
+    rs.cycle = std::atoi(h[3].c_str());
+    rs.R = std::strtod(h[4].c_str(), nullptr);
+    for (auto &b : bodies) {
+        if (!std::getline(f, line)) return false;
+        const auto c = split(line);
+        if (c.size() != 18) return false;
+        auto d = [&](int k) { return std::strtod(c[(size_t)k].c_str(), nullptr); };  // strtod reads C99 hex floats
+        b->Id = std::atoi(c[0].c_str());
+        b->Name = c[1];
+        b->Class = c[2];
+        b->Pinned = c[3] == "1";
+        b->WithTelemetry = c[4] == "1";
+        b->r = d(5);
+        b->fragmenting = c[6] == "1";
+        b->fragInfo = FragInfo{d(7), d(8), d(9), std::atoi(c[10].c_str()), d(11), d(12), d(13)};
+        b->fx = d(14); b->fy = d(15); b->fz = d(16);
+        b->intensity = d(17);
+    }
+    return true;
+}
+
 // ---------------------------------------------------------------- generators (simgen.go), seeded
 namespace {
 struct Rng {
@@ -212,12 +270,17 @@ std::vector<BodyPtr> Generate(const std::string &simName, int bodyCount, Collisi
 
 // ---------------------------------------------------------------- headless run (nbodysim.go:78-133)
 HeadlessResult RunHeadless(std::vector<BodyPtr> bodies, double timeScaling, int runMillis, int maxIterations,
-                           int device, bool quiet)
+                           int device, bool quiet, const RunState *start)
 {
     HeadlessResult out;
     BodyCollection bc(bodies);
     ResultQueueHolder rqh(10);
     ComputationRunner runner(1, timeScaling, false, &rqh, &bc, device);
+    if (start) {  // continue a dumped run: cycle counter, id generator and R are part of its state
+        if (start->cycle >= 0) bc.setCycle(start->cycle);
+        if (start->nextId >= 0) SetNextId(start->nextId);
+        runner.SetCoefficientOfRestitution(start->R);  // picked up at the top of the first cycle, like the gRPC setter
+    }
     if (maxIterations > 0) runner.SetMaxIterations(maxIterations);
     const auto t0 = std::chrono::steady_clock::now();
     runner.Start();
@@ -237,6 +300,10 @@ HeadlessResult RunHeadless(std::vector<BodyPtr> bodies, double timeScaling, int 
     out.fps = out.seconds > 0 ? out.computations / out.seconds : 0;
     out.interactionsPerSec = out.fps * n0 * (n0 - 1);
     out.finalBodies = bc.Count();
+    out.bodies = bc.GetArray();
+    out.state.cycle = bc.cycle();
+    out.state.R = runner.CoefficientOfRestitution();
+    out.state.nextId = NextId();  // consumes one id: only the state of a finished run is read
     if (!quiet) runner.PrintStats();
     return out;
 }

@@ -91,6 +91,7 @@ BodyPtr NewBody(int id, double x, double y, double z, double vx, double vy, doub
                 const std::string &name, const std::string &cls, bool pinned);
 int NextId();          // body.go:316-329
 void ResetIdGenerator();  // tests only
+void SetNextId(int id);    // resume from a state dump: NextId() continues where the dumped run stopped
 
 // ---------------------------------------------------------------- Renderable (cmd/body/renderable.go)
 struct Renderable {
@@ -138,6 +139,7 @@ public:
                           const std::vector<std::string> &mods);
     bool HandleModBody();  // returns true if a request was serviced (device state is then stale)
     int cycle() const { return cycle_; }
+    void setCycle(int c) { cycle_ = c; }  // resume from a state dump (the cycle number seeds fragment())
     int pendingAdds();
     // set by the runner: brings host bodies up to date with the device before they are read
     std::function<void()> syncFromDevice;
@@ -282,14 +284,30 @@ bool WriteCsv(const std::string &csvPath, const std::vector<BodyPtr> &bodies);  
 std::vector<BodyPtr> Generate(const std::string &simName, int bodyCount, CollisionBehavior behavior, BodyColor color,
                               const std::string &simArgs, uint64_t seed);
 
+// What the reference's CSV cannot carry (it is an INPUT format: fromcsv.go:15-47): identity (Id, Name, Class, Pinned,
+// WithTelemetry) and the unexported running state of a Body (r, fragmenting, fragInfo, fx fy fz, intensity), plus the
+// id generator, the collection's cycle counter and the runner's R.  Written next to the final-state CSV
+// (`nbody_server --dump-final-state`), read back with `--resume-state`: together they are a bit-exact checkpoint
+// for any R and with fragmentation in flight (tests/test_checkpoint.py).  One line per body, array order, floats as
+// C99 hex (%a).
+struct RunState {
+    int nextId = -1, cycle = -1;  // -1: leave the id generator / cycle counter as they are
+    double R = 1;
+};
+bool WriteState(const std::string &path, const std::vector<BodyPtr> &bodies, const RunState &rs);
+// applies the sidecar to bodies freshly read by FromCsv (same count, same order); false on any mismatch
+bool ReadState(const std::string &path, std::vector<BodyPtr> &bodies, RunState &rs);
+
 struct HeadlessResult {
     uint64_t computations = 0, iterations = 0;
     double seconds = 0, fps = 0, interactionsPerSec = 0;
     int finalBodies = 0;
+    std::vector<BodyPtr> bodies;  // the collection's array when the run stopped (fragments and added bodies included)
+    RunState state;  // id generator, cycle counter and R when the run stopped
 };
 // nBodySim.Run with render == false (nbodysim.go:78-133): start the runner, drain the result queues,
 // stop after runMillis (or maxIterations if > 0), print stats.
 HeadlessResult RunHeadless(std::vector<BodyPtr> bodies, double timeScaling, int runMillis, int maxIterations,
-                           int device, bool quiet);
+                           int device, bool quiet, const RunState *start = nullptr);
 
 }  // namespace nbodygo

@@ -5,8 +5,10 @@
 // --threads/-t (accepted, no-op), --scaling/-m, --csv/-f, --run-millis/-u, --no-render/-r
 // (always on: there is no renderer here), --no-barnes-hut (always brute force).
 // Additions: --gpu=<device>, --seed=<n>, --iterations=<n>, --dump-csv=<path> (initial bodies),
-// --dump-final-csv=<path> (surviving bodies after the run: a restartable checkpoint, the reference
-// has none).
+// --dump-final-csv=<path> (surviving bodies after the run in the reference's CSV format),
+// --dump-final-state=<path> / --resume-state=<path> (the sidecar with what that CSV cannot carry: together a
+// bit-exact checkpoint, the reference has none), --restitution=<R> (the runner's R; the reference sets it over
+// gRPC only).
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -18,7 +20,9 @@ using namespace nbodygo;
 
 int main(int argc, char **argv)
 {
-    std::string simName = "Sim1", simArgs, csvPath, dumpCsv, dumpFinalCsv;
+    std::string simName = "Sim1", simArgs, csvPath, dumpCsv, dumpFinalCsv, dumpFinalState, resumeState;
+    double restitution = 1;
+    bool haveR = false;
     CollisionBehavior behavior = Elastic;
     BodyColor color = Random;
     int bodyCount = 1000, runMillis = -1, iterations = 0, device = 0;
@@ -51,6 +55,9 @@ int main(int argc, char **argv)
         else if (a == "--iterations") iterations = std::atoi(val().c_str());
         else if (a == "--dump-csv") dumpCsv = val();
         else if (a == "--dump-final-csv") dumpFinalCsv = val();
+        else if (a == "--dump-final-state") dumpFinalState = val();
+        else if (a == "--resume-state") resumeState = val();
+        else if (a == "--restitution") { restitution = std::atof(val().c_str()); haveR = true; }
         else {
             std::fprintf(stderr, "unknown option %s\n", a.c_str());
             return 2;
@@ -70,14 +77,34 @@ int main(int argc, char **argv)
         }
     }
     if (!dumpCsv.empty()) WriteCsv(dumpCsv, bodies);
+    RunState start;
+    bool haveStart = false;
+    if (!resumeState.empty()) {
+        if (!ReadState(resumeState, bodies, start)) {
+            std::fprintf(stderr, "ERROR: %s does not match the bodies read from the CSV\n", resumeState.c_str());
+            return 1;
+        }
+        haveStart = true;
+    }
+    if (haveR) {  // overrides the R of a resumed run, like a set-restitution-coefficient call before its first cycle
+        start.R = restitution;
+        haveStart = true;
+    }
     try {
-        const HeadlessResult r = RunHeadless(bodies, scaling, runMillis, iterations, device, false);
+        const HeadlessResult r = RunHeadless(bodies, scaling, runMillis, iterations, device, false,
+                                             haveStart ? &start : nullptr);
         std::printf("bodies: %zu -> %d\ninteractions/s: %.6e\n", bodies.size(), r.finalBodies, r.interactionsPerSec);
         if (!dumpFinalCsv.empty()) {
             std::vector<BodyPtr> alive;
-            for (auto &b : bodies)
+            for (auto &b : r.bodies)
                 if (b->Exists) alive.push_back(b);
             WriteCsv(dumpFinalCsv, alive);
+        }
+        if (!dumpFinalState.empty()) {
+            std::vector<BodyPtr> alive;
+            for (auto &b : r.bodies)
+                if (b->Exists) alive.push_back(b);
+            WriteState(dumpFinalState, alive, r.state);
         }
     } catch (const std::exception &e) {
         std::fprintf(stderr, "%s\n", e.what());

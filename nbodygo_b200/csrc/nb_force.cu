@@ -40,6 +40,9 @@
 // rank count.
 //
 // This file is compiled with -fmad=false: every FMA below is explicit.
+#if defined(NB_EXP_CONV_PROBE) && NB_EXP_CONV_PROBE
+#include <cstdio>
+#endif
 #include "nb_internal.cuh"
 
 namespace nb {
@@ -136,6 +139,9 @@ __device__ __forceinline__ double rsqrt_seed_lo(double x, unsigned lo)
 #endif
 #ifndef NB_EXP_KZ_UNI
 #define NB_EXP_KZ_UNI 0
+#endif
+#ifndef NB_EXP_CONV_PROBE
+#define NB_EXP_CONV_PROBE 0
 #endif
 #ifndef NB_EXP_UNR4
 #define NB_EXP_UNR4 1
@@ -622,6 +628,17 @@ __global__ void __launch_bounds__(NT, MINB) k_force(const __grid_constant__ Step
             az[r] = __dadd_rn(az[r], tz[r]);
         }
         __syncthreads();  // every warp is done with stage s before it is refilled
+#if NB_EXP_CONV_PROBE  // development: is the warp converged when it leaves the barrier after a redo?
+        {
+            const unsigned am = __activemask();
+            bool redo = false;
+#pragma unroll
+            for (int r = 0; r < R; ++r) redo |= lo[r] < thr[r];
+            const unsigned vote = __ballot_sync(am, redo);
+            if (vote && (tid & 31) == __ffs(am) - 1)
+                printf("CONV %s mask=%08x redo=%08x\n", am == 0xffffffffu ? "full" : "PARTIAL", am, vote);
+        }
+#endif
     }
 
     // one partial-sum slot per (chunk, body); G*m_i is applied by the integrate kernel

@@ -255,6 +255,49 @@ static void TestCsvRoundTrip()
     CHECK(Generate("Sim5", 0, Elastic, Random, "", 1).back()->Behavior == Fragment);
 }
 
+// CSV + state sidecar together restore a running body exactly (what the CSV drops: identity, r, fragmenting,
+// fragInfo, forces, intensity; plus id generator, cycle counter and R) and a sidecar of another CSV is refused
+static void TestStateSidecar()
+{
+    ResetIdGenerator();
+    auto bodies = Generate("Sim3", 51, Elastic, Random, "", 7);
+    for (size_t i = 0; i < bodies.size(); ++i) {
+        Body &b = *bodies[i];
+        b.Id = 1000 + (int)(3 * i);
+        b.Name = i % 5 == 0 ? "n" + std::to_string(i) : "";
+        b.Class = i % 7 == 0 ? "asteroid" : "";
+        b.WithTelemetry = i % 4 == 1;
+        b.r = 0.1 + 1e-3 * (double)i;
+        b.fx = std::ldexp(1.0 / 3.0, (int)i); b.fy = -b.fx * 1.0000000000000002; b.fz = 5e-324;
+        if (i % 6 == 2) {
+            b.Behavior = Fragment;
+            b.fragmenting = true;
+            b.fragInfo = FragInfo{b.Radius, b.Radius / 3, b.Mass / 7, 17 + (int)i, b.X, b.Y, b.Z};
+        }
+    }
+    RunState rs;
+    rs.nextId = 4242; rs.cycle = 99; rs.R = 0.8;
+    CHECK(WriteCsv("/tmp/nb_host_state.csv", bodies) && WriteState("/tmp/nb_host_state.nbs", bodies, rs));
+    auto back = FromCsv("/tmp/nb_host_state.csv", 1000, Elastic, Random);
+    RunState rb;
+    CHECK(back.size() == bodies.size() && ReadState("/tmp/nb_host_state.nbs", back, rb));
+    CHECK(rb.nextId == 4242 && rb.cycle == 99 && rb.R == 0.8);
+    for (size_t i = 0; i < bodies.size() && i < back.size(); ++i) {
+        const Body &a = *bodies[i], &b = *back[i];
+        CHECK(a.Id == b.Id && a.Name == b.Name && a.Class == b.Class && a.Pinned == b.Pinned &&
+              a.WithTelemetry == b.WithTelemetry);
+        CHECK(a.r == b.r && a.fx == b.fx && a.fy == b.fy && a.fz == b.fz && a.intensity == b.intensity);
+        CHECK(a.fragmenting == b.fragmenting && a.fragInfo.fragments == b.fragInfo.fragments &&
+              a.fragInfo.radius == b.fragInfo.radius && a.fragInfo.newRadius == b.fragInfo.newRadius &&
+              a.fragInfo.mass == b.fragInfo.mass && a.fragInfo.x == b.fragInfo.x && a.fragInfo.z == b.fragInfo.z);
+        CHECK(a.X == b.X && a.Vz == b.Vz && a.Mass == b.Mass && a.Behavior == b.Behavior);
+    }
+    auto fewer = FromCsv("/tmp/nb_host_state.csv", 50, Elastic, Random);
+    CHECK(!ReadState("/tmp/nb_host_state.nbs", fewer, rb));               // body count differs
+    CHECK(!ReadState("/tmp/nb_host_state.csv", back, rb));                // not a sidecar
+    CHECK(!ReadState("/tmp/no_such_file.nbs", back, rb));
+}
+
 static void TestNoDeviceFailsLoudly()
 {
     // without a device the runner must refuse to start: there is no CPU fallback
@@ -455,7 +498,7 @@ int main(int argc, char **argv)
                           {"TestModByClass", TestModByClass}, {"TestSubsume", TestSubsume},
                           {"TestFragmentHostPath", TestFragmentHostPath},
                           {"TestResultQueueHolder", TestResultQueueHolder}, {"TestResultQueueSoak", TestResultQueueSoak},
-                          {"TestCsvRoundTrip", TestCsvRoundTrip}};
+                          {"TestCsvRoundTrip", TestCsvRoundTrip}, {"TestStateSidecar", TestStateSidecar}};
     std::vector<T> nodev = {{"TestNoDeviceFailsLoudly", TestNoDeviceFailsLoudly}};
     std::vector<T> gpu = {{"TestWpCompute", TestWpCompute}, {"TestRunnerSetters", TestRunnerSetters},
                           {"TestCollide", TestCollide}, {"TestControlWindow", TestControlWindow},

@@ -19,7 +19,7 @@ def _run(mode, timeout=600):
 def test_host_unit_tests_cpu():
     r = _run("cpu")
     assert r.returncode == 0, r.stdout[-3000:]
-    assert "18 tests, 0 failures" in r.stdout
+    assert "19 tests, 0 failures" in r.stdout
 
 
 def test_runner_refuses_to_start_without_device():

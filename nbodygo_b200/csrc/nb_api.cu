@@ -93,6 +93,7 @@ struct nb_sim {
     int force_R = 0;
     bool uniform_tiles = true;  // NB_UNIFORM_TILES=0 keeps every tile on the general (per-body mass) pass
     int res_cluster = 8;        // CTAs of the resolve cluster (portable maximum); NB_RES_CLUSTER=1: one CTA as in round 1
+    int res_fast = 1;           // short event lists are scheduled in shared memory; NB_RES_FAST=0: always the general path
     StepParams last_params{};
     // fused peer-memory exchange (K4 pushes the shard state into every peer's replica)
     bool peer_push = false;
@@ -233,6 +234,7 @@ extern "C" int nb_create(int device, int64_t capacity, int64_t pair_capacity, nb
     if (const char *g = getenv("NB_GRAPH")) h->graphs_enabled = atoi(g) != 0;
     if (const char *u = getenv("NB_UNIFORM_TILES")) h->uniform_tiles = atoi(u) != 0;
     if (const char *c = getenv("NB_RES_CLUSTER")) h->res_cluster = std::max(1, std::min(8, atoi(c)));
+    if (const char *c = getenv("NB_RES_FAST")) h->res_fast = atoi(c) != 0;
     auto bail = [&](const char *what, cudaError_t ce) {
         g_create_err = std::string(what) + ": " + cudaGetErrorString(ce);
         free_all(h);
@@ -759,6 +761,7 @@ extern "C" int nb_step(nb_handle h, double time_scaling, double R, uint32_t opts
     p.opts = opts;
     p.uniform_tiles = h->uniform_tiles ? 1 : 0;
     p.res_cluster = h->res_cluster;
+    p.res_fast = h->res_fast;
     p.ts = time_scaling;
     p.R = R;
     int rc = ensure_partials(h, (long long)p.n_chunks * p.n_pad_local);

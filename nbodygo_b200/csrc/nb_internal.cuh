@@ -159,6 +159,7 @@ struct StepParams {
     unsigned opts;
     int uniform_tiles;   // 1: K0 marks uniform-mass tiles and K1 hoists the mass out of their pair loop
     int res_cluster;     // CTAs of the resolve cluster (1..8)
+    int res_fast;        // 1: event lists of up to 64 entries are scheduled in shared memory (NB_RES_FAST=0: never)
     double ts, R;
 };
 

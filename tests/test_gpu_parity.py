@@ -723,3 +723,43 @@ def test_resolve_cluster_equals_single_cta(capi, monkeypatch):
             for x, y in zip(a[4:9], c[4:9]):
                 assert np.array_equal(x.view(np.uint8), y.view(np.uint8))
             assert a[9] == c[9]
+
+
+def test_short_event_lists_use_the_shared_memory_schedule_with_the_same_bits(capi, monkeypatch):
+    """Event lists of up to 64 entries are scheduled in shared memory by the first CTA of K3 (no per-body lists in
+    global memory); the readiness rule is the same, so rounds, counters, host records and every state bit must equal
+    the general path's (NB_RES_FAST=0).  Small dense clouds: chains through shared bodies (several rounds), subsume
+    and fragment decisions, lists just under, at and just over the limit."""
+    rng = np.random.default_rng(53)
+    seen_rounds, seen_sizes = set(), []
+    for n, side, seed in ((150, 30.0, 1), (260, 38.0, 2), (400, 48.0, 3), (90, 20.0, 4), (320, 40.0, 5)):
+        b = clouds.uniform_cube(n, side, 1.2, 1e12, vmax=200.0, seed=60 + seed)
+        b.radius[:] = rng.uniform(0.6, 2.2, n)
+        b.behavior[rng.random(n) < 0.12] = SUBSUME
+        b.behavior[rng.random(n) < 0.12] = FRAGMENT
+        b.frag_factor[:] = 0.05
+        b.frag_step[:] = 100.0
+        outs = []
+        for fast in ("1", "0"):
+            monkeypatch.setenv("NB_RES_FAST", fast)          # read at nb_create
+            sim = capi.Sim(n)
+            sim.upload(b)
+            log = []
+            for _ in range(4):
+                res = sim.step(2e-4, 0.85)
+                st = sim.download()
+                log.append((res.n_pairs, res.n_resolved, res.n_subsumed, res.resolve_rounds, res.n_host_events,
+                            st.vx.copy(), st.vy.copy(), st.vz.copy(), st.mass.copy(), st.flags.copy(),
+                            st.behavior.copy(), [tuple(e) for e in sim.host_events().tolist()],
+                            sorted(map(tuple, sim.pairs().tolist()))))
+            sim.close()
+            outs.append(log)
+        for a, c in zip(*outs):
+            assert a[:5] == c[:5]
+            for x, y in zip(a[5:11], c[5:11]):
+                assert np.array_equal(x.view(np.uint8), y.view(np.uint8))
+            assert a[11] == c[11] and a[12] == c[12]
+            seen_rounds.add(a[3])
+            seen_sizes.append(a[0] + a[2])
+    assert any(0 < k <= 64 for k in seen_sizes) and any(k > 64 for k in seen_sizes)   # both sides of the limit
+    assert max(seen_rounds) >= 3                                                       # chains, not just isolated pairs

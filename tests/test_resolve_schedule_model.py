@@ -76,3 +76,47 @@ def test_symmetric_pairs_resolve_in_two_rounds_and_chains_in_their_length():
     chain = [(k, k + 1) for k in range(30)]
     state, rounds = wavefront(31, chain, 2)
     assert rounds == 30 and state == serial(31, chain)
+
+
+def short_list_schedule(n, events, shuffle_seed):
+    """The shared-memory schedule K3 uses for lists of up to 64 events (nb_resolve.cu, `FAST_MAX`): no per-body heads;
+    an event is ready when no pending event with a LARGER key shares one of its bodies.  Returns the state and the
+    list of rounds (each a set of events)."""
+    state = list(range(1, n + 1))
+    pending = list(set(events))
+    random.Random(shuffle_seed).shuffle(pending)
+    rounds = []
+    while pending:
+        ready = [e for e in pending
+                 if not any(key(*o) > key(*e) and (o[0] in e or o[1] in e) for o in pending)]
+        assert ready
+        for i, j in ready:
+            apply_event(state, i, j, key(i, j) % 9973)
+        rounds.append(set(ready))
+        pending = [e for e in pending if e not in rounds[-1]]
+    return state, rounds
+
+
+def wavefront_rounds(n, events):
+    pending, rounds = set(events), []
+    while pending:
+        head = {}
+        for i, j in pending:
+            head[i] = max(head.get(i, -1), key(i, j))
+            head[j] = max(head.get(j, -1), key(i, j))
+        ready = {(i, j) for i, j in pending if head[i] == key(i, j) and head[j] == key(i, j)}
+        rounds.append(ready)
+        pending -= ready
+    return rounds
+
+
+@settings(max_examples=300, deadline=None, derandomize=True)
+@given(pairs)
+def test_short_list_rule_makes_the_same_rounds_as_the_heads(case):
+    """Same events in the same rounds (so `resolve_rounds` and every result bit agree), same final state as the
+    serial order — the GPU test compares the two kernel paths, this one the two rules."""
+    n, events, seed = case
+    events = events[:64]
+    state, rounds = short_list_schedule(n, events, seed)
+    assert rounds == wavefront_rounds(n, events)
+    assert state == serial(n, events)
